@@ -1,0 +1,316 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Compiles the UNMODIFIED reference translation unit (/root/reference/NDP-5_6_7.cpp, which
+// pulls ClauseSetPool.hpp) against oracle/shim/{mpi.h,gmpxx.h} and exports its own hot-path
+// functions behind a C ABI so tests (ctypes) and the CPU baseline can call the real thing:
+//   parseDimacsString (NDP:619)  choice (NDP:753)  ResolutionStep (NDP:700)
+//   ResolutionStepWithConflict (NDP:654)  Satisfy_iterative_BFS (NDP:881)
+//   Satisfy_iterative (NDP:784)  save/readBFSResults (NDP:564,600)  convert (NDP:1017)
+//   createProblemID/formatFilename/createBFSFilename/formatDuration (NDP:423-562)
+//   calculate_max_iterations (NDP:1031)  generate_output (NDP:1127)
+// Build: oracle/Makefile -> oracle/_ref/libndp_ref.so (+ _prof variant with -DENABLE_PROFILING,
+// whose PROFILE_SCOPE call counts give DFS node counts).
+//
+// Two deliberate neutralisations, both outside the reference source:
+//  * `main` is renamed so the TU can live in a shared object;
+//  * the TU's global initialiser dup2()s /dev/null over stderr (NDP:307-308); inside a
+//    pytest process that would silence the whole test run, so dup2 is macro-diverted to a
+//    no-op for the duration of the include.
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <signal.h>
+#include <time.h>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <iomanip>
+#include <map>
+#include <sstream>
+
+static inline int ndp_harness_dup2_noop(int, int) { return 0; }
+#define dup2(a, b) ndp_harness_dup2_noop(a, b)
+#define main ndp_reference_main
+#include "NDP-5_6_7.cpp"   // resolved through -I/root/reference ; unmodified
+#undef main
+#undef dup2
+
+namespace {
+using Frontier = std::vector<std::pair<ClauseSet, std::vector<int>>>;
+
+ClauseSet to_set(const int32_t* c3, size_t n) {
+    ClauseSet s(n);
+    for (size_t k = 0; k < n; ++k) { s[k].l[0] = c3[3 * k]; s[k].l[1] = c3[3 * k + 1]; s[k].l[2] = c3[3 * k + 2]; }
+    return s;
+}
+void from_set(const ClauseSet& s, int32_t* out) {
+    for (size_t k = 0; k < s.size(); ++k) { out[3 * k] = s[k].l[0]; out[3 * k + 1] = s[k].l[1]; out[3 * k + 2] = s[k].l[2]; }
+}
+Frontier drain(std::queue<std::pair<ClauseSet, std::vector<int>>>& q) {
+    Frontier f;
+    f.reserve(q.size());
+    while (!q.empty()) { f.emplace_back(std::move(q.front())); q.pop(); }
+    return f;
+}
+size_t put(const std::string& s, char* out, size_t cap) {
+    if (out && cap) { size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(out, s.data(), n); out[n] = 0; }
+    return s.size();
+}
+double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+long dfs_node_count() {
+#ifdef ENABLE_PROFILING
+    std::lock_guard<std::mutex> lock(profiler_mutex);
+    return profiler_data["Satisfy_iterative_loop_with_pool"].second;
+#else
+    return -1;
+#endif
+}
+}  // namespace
+
+extern "C" {
+
+int ref_profiling_enabled(void) {
+#ifdef ENABLE_PROFILING
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+// ---- parser / primitives -------------------------------------------------------------------
+size_t ref_parse_dimacs(const char* text, int32_t* out3, size_t cap_clauses) {
+    ClauseSet s = parseDimacsString(std::string(text));
+    if (out3 && s.size() <= cap_clauses) from_set(s, out3);
+    return s.size();
+}
+int ref_choice(const int32_t* c3, size_t n) { return choice(to_set(c3, n)); }
+
+// out_la/out_ra must hold 3*n ints each; with_conflict selects NDP:654 vs NDP:700.
+void ref_resolution_step(const int32_t* c3, size_t n, int i, int with_conflict, int32_t* out_la, size_t* n_la,
+                         int32_t* out_ra, size_t* n_ra, int* conflict_la, int* conflict_ra) {
+    ClauseSet A = to_set(c3, n);
+    if (with_conflict) {
+        auto br = ResolutionStepWithConflict(A, i);
+        from_set(br.first.cs, out_la); *n_la = br.first.cs.size(); *conflict_la = br.first.conflict;
+        from_set(br.second.cs, out_ra); *n_ra = br.second.cs.size(); *conflict_ra = br.second.conflict;
+    } else {
+        auto br = ResolutionStep(A, i);
+        from_set(br.first, out_la); *n_la = br.first.size(); *conflict_la = -1;
+        from_set(br.second, out_ra); *n_ra = br.second.size(); *conflict_ra = -1;
+    }
+}
+
+// ---- BFS -----------------------------------------------------------------------------------
+void* ref_bfs(const int32_t* c3, size_t n, int max_iterations, int override_max_iterations, int max_queues,
+              int* iterations, int* task_count, size_t* initial_queue_size, double* seconds) {
+    ClauseSet A = to_set(c3, n);
+    int it = 0;
+    size_t iq = 0;
+    double t0 = now_s();
+    // world_rank=1: identical result, suppresses the per-expansion progress line (NDP:928-933)
+    auto res = Satisfy_iterative_BFS(A, max_iterations, override_max_iterations != 0, it, max_queues, 1, iq);
+    double t1 = now_s();
+    if (iterations) *iterations = it;
+    if (task_count) *task_count = res.second;
+    if (initial_queue_size) *initial_queue_size = iq;
+    if (seconds) *seconds = t1 - t0;
+    return new Frontier(drain(res.first));
+}
+size_t ref_frontier_size(void* h) { return static_cast<Frontier*>(h)->size(); }
+size_t ref_frontier_nclauses(void* h, size_t k) { return (*static_cast<Frontier*>(h))[k].first.size(); }
+size_t ref_frontier_nchoices(void* h, size_t k) { return (*static_cast<Frontier*>(h))[k].second.size(); }
+void ref_frontier_copy(void* h, size_t k, int32_t* clauses3, int32_t* choices) {
+    auto& e = (*static_cast<Frontier*>(h))[k];
+    if (clauses3) from_set(e.first, clauses3);
+    if (choices) for (size_t j = 0; j < e.second.size(); ++j) choices[j] = e.second[j];
+}
+void ref_frontier_free(void* h) { delete static_cast<Frontier*>(h); }
+
+// ---- DFS -----------------------------------------------------------------------------------
+// returns number of models (0 => UNSAT); the first model is copied to `model` (<= cap ints).
+int ref_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, size_t cap, size_t* model_len,
+            long* nodes) {
+    long before = dfs_node_count();
+    auto res = Satisfy_iterative(to_set(c3, n), first_assignment != 0);
+    long after = dfs_node_count();
+    if (nodes) *nodes = before < 0 ? -1 : after - before;
+    if (model_len) *model_len = res.empty() ? 0 : res[0].size();
+    if (!res.empty() && model) for (size_t j = 0; j < res[0].size() && j < cap; ++j) model[j] = res[0][j];
+    return (int)res.size();
+}
+
+// DFS over a whole frontier with `workers` forked processes pulling the next index from a
+// shared atomic counter: the reference's FIFO one-task-per-request policy (NDP:1322-1346)
+// without the MPI messages.  early_exit!=0 mirrors NDP:1297-1303/1447: the job ends at the
+// first reported model.  verdict[k]: 0 UNSAT, 1 SAT, 2 not run.  Returns wall seconds.
+// winner/model: lowest-index SAT subproblem's full model = choices_k ++ dfs choices (NDP:1430-1431).
+double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int early_exit, uint8_t* verdict,
+                        long* winner, int32_t* model, size_t model_cap, size_t* model_len) {
+    Frontier& f = *static_cast<Frontier*>(h);
+    if (first_k > f.size()) first_k = f.size();
+    if (count > f.size() - first_k) count = f.size() - first_k;
+    if (workers < 1) workers = 1;
+    const size_t model_ints = 1u << 22;
+    struct Shared { std::atomic<long> next; std::atomic<long> found; std::atomic<long> model_off; };
+    size_t bytes = sizeof(Shared) + count + model_ints * sizeof(int32_t) + count * sizeof(long) * 2;
+    char* mem = (char*)mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    Shared* sh = new (mem) Shared;
+    sh->next = 0; sh->found = 0; sh->model_off = 0;
+    uint8_t* v = (uint8_t*)(mem + sizeof(Shared));
+    size_t voff = (sizeof(Shared) + count + 15) & ~size_t(15);
+    long* moff = (long*)(mem + voff);            // per subproblem: offset, len into models
+    int32_t* models = (int32_t*)(mem + voff + count * sizeof(long) * 2);
+    memset(v, 2, count);
+    double t0 = now_s();
+    std::vector<pid_t> pids;
+    for (int w = 0; w < workers; ++w) {
+        pid_t p = fork();
+        if (p == 0) {
+            for (;;) {
+                if (early_exit && sh->found.load()) break;
+                long k = sh->next.fetch_add(1);
+                if (k >= (long)count) break;
+                auto res = Satisfy_iterative(f[first_k + k].first, true);
+                if (!res.empty()) {
+                    const auto& ch = f[first_k + k].second;
+                    long len = (long)(ch.size() + res[0].size());
+                    long off = sh->model_off.fetch_add(len);
+                    if (off + len <= (long)model_ints) {
+                        for (size_t j = 0; j < ch.size(); ++j) models[off + j] = ch[j];
+                        for (size_t j = 0; j < res[0].size(); ++j) models[off + ch.size() + j] = res[0][j];
+                        moff[2 * k] = off; moff[2 * k + 1] = len;
+                    } else { moff[2 * k] = -1; moff[2 * k + 1] = 0; }
+                    v[k] = 1;
+                    sh->found.fetch_add(1);
+                } else {
+                    v[k] = 0;
+                }
+            }
+            _exit(0);
+        }
+        pids.push_back(p);
+    }
+    double t_end = 0;
+    if (early_exit) {
+        // the reference terminates the job as soon as the first model is reported
+        for (;;) {
+            if (sh->found.load() > 0) { t_end = now_s(); for (pid_t p : pids) kill(p, SIGKILL); break; }
+            int st; pid_t r = waitpid(-1, &st, WNOHANG);
+            if (r > 0) { pids.erase(std::remove(pids.begin(), pids.end(), r), pids.end()); if (pids.empty()) break; }
+            else { timespec ts{0, 200000}; nanosleep(&ts, nullptr); }
+        }
+    }
+    for (pid_t p : pids) { int st; waitpid(p, &st, 0); }
+    if (t_end == 0) t_end = now_s();
+    long win = -1;
+    for (size_t k = 0; k < count; ++k) if (v[k] == 1) { win = (long)k; break; }
+    if (verdict) memcpy(verdict, v, count);
+    if (winner) *winner = win < 0 ? -1 : (long)first_k + win;
+    if (model_len) *model_len = 0;
+    if (win >= 0 && moff[2 * win] >= 0) {
+        size_t len = (size_t)moff[2 * win + 1];
+        if (model_len) *model_len = len;
+        if (model) for (size_t j = 0; j < len && j < model_cap; ++j) model[j] = models[moff[2 * win] + j];
+    }
+    munmap(mem, bytes);
+    return t_end - t0;
+}
+
+// ---- persistence (reference writer/reader, NDP:487-612) ------------------------------------
+size_t ref_save_bfs(void* h, const char* script_name, const char* filename, const char* problem_id, const char* flag,
+                    const char* outdir, double bfs_time, char* out_name, size_t cap) {
+    std::queue<std::pair<ClauseSet, std::vector<int>>> q;
+    for (auto& e : *static_cast<Frontier*>(h)) q.push(e);
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    saveBFSResults(q, script_name, filename, problem_id, flag, outdir, bfs_time);
+    std::cout.rdbuf(old);
+    return put(createBFSFilename(script_name, filename, problem_id, flag), out_name, cap);
+}
+void* ref_read_bfs(const char* path, double* bfs_time) {
+    try {
+        auto res = readBFSResults(path);
+        if (bfs_time) *bfs_time = res.second;
+        return new Frontier(drain(res.first));
+    } catch (const std::exception&) { return nullptr; }
+}
+
+// ---- naming / formatting -------------------------------------------------------------------
+size_t ref_create_problem_id(const char* n, int bits, int world, const char* utc, char* out, size_t cap) {
+    return put(createProblemID(n, bits, world, utc), out, cap);
+}
+size_t ref_format_filename(const char* script, const char* file, const char* pid, const char* flag, char* out, size_t cap) {
+    return put(formatFilename(script, file, pid, flag), out, cap);
+}
+size_t ref_create_bfs_filename(const char* script, const char* file, const char* pid, const char* flag, char* out, size_t cap) {
+    return put(createBFSFilename(script, file, pid, flag), out, cap);
+}
+size_t ref_format_duration(double s, char* out, size_t cap) { return put(formatDuration(s), out, cap); }
+size_t ref_format_percentage(double a, double b, char* out, size_t cap) { return put(formatPercentage(a, b), out, cap); }
+size_t ref_format_vector(const int32_t* v, size_t n, char* out, size_t cap) {
+    return put(formatVector(std::vector<int>(v, v + n)), out, cap);
+}
+int ref_calculate_max_iterations(int world, int clauses, int vars, int bits) {
+    return calculate_max_iterations(world, clauses, vars, bits);
+}
+// header scrape exactly as main() does it (NDP:1590-1615) + ExtractInputsFromDimacs (NDP:946)
+int ref_scrape_header(const char* text, int* num_vars, int* num_clauses, int* num_bits, char* product, size_t cap,
+                      int32_t* v1, size_t* n1, int32_t* v2, size_t* n2, size_t vcap) {
+    std::string fileContent(text);
+    std::smatch match;
+    std::regex regex_product(R"(Circuit for product = ([0-9]+) \[)");
+    std::regex regex_problem(R"(p cnf ([0-9]+) ([0-9]+))");
+    *num_bits = 0;
+    if (!std::regex_search(fileContent, match, regex_problem)) return 1;
+    *num_vars = std::stoi(match[1].str());
+    *num_clauses = std::stoi(match[2].str());
+    std::regex regex_bits(R"(Variables for second input \[msb,...,lsb\]: \[.*?,\s*(\d+)\])");
+    if (std::regex_search(fileContent, match, regex_bits)) *num_bits = std::stoi(match[1].str());
+    if (!std::regex_search(fileContent, match, regex_product)) return 2;
+    put(match[1].str(), product, cap);
+    std::vector<int> a, b;
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    ExtractInputsFromDimacs(fileContent, a, b);
+    std::cout.rdbuf(old);
+    *n1 = a.size(); *n2 = b.size();
+    for (size_t j = 0; j < a.size() && j < vcap; ++j) v1[j] = a[j];
+    for (size_t j = 0; j < b.size() && j < vcap; ++j) v2[j] = b[j];
+    return 0;
+}
+// factor decode + GMP check (NDP:1008-1027,1153); returns 1 if d1*d2 == N
+int ref_convert(const int32_t* model, size_t len, const int32_t* v1, size_t n1, const int32_t* v2, size_t n2,
+                const char* input_number, char* d1, char* d2, size_t cap) {
+    std::vector<std::vector<int>> v{std::vector<int>(model, model + len)};
+    auto pr = convert(v, std::vector<int>(v1, v1 + n1), std::vector<int>(v2, v2 + n2));
+    put(pr.first.get_str(), d1, cap);
+    put(pr.second.get_str(), d2, cap);
+    mpz_class N;
+    N.set_str(input_number, 10);
+    return pr.first * pr.second == N ? 1 : 0;
+}
+// full report block (NDP:1127-1205); returns the text the reference prints to stdout and
+// writes the .txt file into outdir as the reference does.
+size_t ref_generate_output(int solution_found, const int32_t* model, size_t len, double bfs_s, double dfs_s,
+                           int num_bits, int num_vars, int num_clauses, const char* input_number, const int32_t* v1,
+                           size_t n1, const int32_t* v2, size_t n2, const char* script, const char* filename,
+                           const char* cli_flag, const char* outdir, int iterations, size_t initial_queue_size,
+                           int world_rank, int world_size, int final_queue_size, char* out, size_t cap) {
+    std::vector<std::vector<int>> sols;
+    if (solution_found) sols.emplace_back(model, model + len);
+    mpz_class N;
+    N.set_str(input_number, 10);
+    std::vector<int> a(v1, v1 + n1), b(v2, v2 + n2);
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream cap_ss;
+    std::cout.rdbuf(cap_ss.rdbuf());
+    generate_output(solution_found != 0, sols, std::chrono::duration<double>(bfs_s), std::chrono::duration<double>(dfs_s),
+                    num_bits, num_vars, num_clauses, N, a, b, script, filename, cli_flag, outdir, iterations,
+                    initial_queue_size, world_rank, world_size, final_queue_size);
+    std::cout.rdbuf(old);
+    return put(cap_ss.str(), out, cap);
+}
+}  // extern "C"
