@@ -1,0 +1,124 @@
+/* include/ndp_b200.h -- C ABI of the B200-native NDP hot path (BFS granulation -> DFS).
+ *
+ * The reference (GridSAT NDP 5.6.7) has no plugin/FFI layer; its hot path is entered at two
+ * C++ call sites inside one translation unit.  Each entry point below names the reference
+ * interface it replaces (file:line into the reference tree; NDP = NDP-5_6_7.cpp,
+ * CSP = ClauseSetPool.hpp).  Plain pointers and sizes only; no exceptions cross this boundary;
+ * every function returns an ndp_status and leaves a message for ndp_last_error().
+ *
+ * Clause arrays are n x 3 row-major int32, exactly the layout flattenClauseSet produces
+ * (NDP:1207-1215): literal 0 means "already false / padding" (CSP:37-39); a unit clause x is
+ * {0,0,x} (NDP:632-634).
+ *
+ * There is no CPU fallback: every compute entry point fails with NDP_E_CUDA when no sm_100
+ * device (or no CUDA driver) is present.
+ */
+#ifndef NDP_B200_H
+#define NDP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ndp_status {
+    NDP_OK = 0,
+    NDP_E_INVALID = 1,      /* bad argument (null pointer, index out of range, ...) */
+    NDP_E_UNSUPPORTED = 2,  /* input outside what the kernels pack (|literal| > 32767, ...) */
+    NDP_E_CUDA = 3,         /* CUDA runtime error / no usable device */
+    NDP_E_NOMEM = 4         /* device arena or host allocation failed */
+} ndp_status;
+
+/* verdict bytes written by the DFS entry points */
+enum { NDP_UNSAT = 0, NDP_SAT = 1, NDP_NOT_RUN = 2 };
+
+/* Opaque frontier: the queue<pair<ClauseSet, vector<int>>> that Satisfy_iterative_BFS returns
+ * (NDP:881-882, 943).  Owned by the library; clause sets live in a device arena of packed
+ * clause slots (the device-side replacement of ClauseSetPool, CSP:43-69). */
+typedef struct ndp_frontier ndp_frontier;
+
+typedef struct ndp_stats {
+    uint64_t nodes;          /* DFS nodes = Satisfy_iterative loop iterations (NDP:801) */
+    uint64_t clause_evals;   /* sum of |A| over nodes that ran the resolution pass (NDP:664) */
+    uint64_t rebuilds;       /* sibling re-materialisations (engine detail, not in the reference) */
+    double kernel_ms;        /* device time of the DFS kernel(s), CUDA events */
+    double h2d_ms, d2h_ms;   /* transfers done inside the call */
+    uint64_t launches;       /* kernels launched by the call */
+} ndp_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Select the CUDA device used by subsequent calls from this thread's process (default 0).
+ * Replaces nothing in the reference (MPI rank placement, NDP:1542-1545, is out of scope). */
+int ndp_set_device(int device);
+int ndp_device_count(int* count);
+const char* ndp_last_error(void);
+const char* ndp_version(void);
+
+/* ---- BFS granulation --------------------------------------------------------------------
+ * Replaces the call at NDP:1651:
+ *   Satisfy_iterative_BFS(clauses, depth, override_max_iterations, iterations, max_queues,
+ *                         world_rank, initial_queue_size)            (definition NDP:881-944)
+ * Same argument meaning: max_iterations is the -d node-expansion budget (NDP:935), max_queues
+ * the -q queue-size threshold tested before each pop (NDP:894), override_max_iterations what
+ * -q sets (NDP:1512).  Outputs: *iterations (NDP:926), *task_count (second member of the
+ * returned pair, NDP:943), *initial_queue_size with the reference's in/out rule "assign only
+ * if it was 0" (NDP:939-941).  The frontier holds the same subproblems in the same order. */
+int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int override_max_iterations,
+            int max_queues, ndp_frontier** out, int* iterations, int* task_count, size_t* initial_queue_size);
+
+/* BFS clause evaluations (sum of |A| over expanded nodes) and device time of the last ndp_bfs
+ * that produced this frontier; 0 for frontiers built by ndp_frontier_from_host. */
+int ndp_frontier_bfs_stats(const ndp_frontier* f, uint64_t* clause_evals, double* kernel_ms, uint64_t* launches);
+
+size_t ndp_frontier_size(const ndp_frontier* f);
+
+/* Element k of the queue in FIFO order: the materialised clause set (zeros included) and the
+ * choices that led to it -- what serializeBFSResults walks (NDP:487-510) and what the
+ * dispatcher ships to a worker (NDP:1337-1346).  Returned pointers are library-owned and stay
+ * valid until the next ndp_frontier_get on the same frontier or ndp_frontier_free. */
+int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t* n_clauses,
+                     const int32_t** choices, size_t* n_choices);
+
+/* Sizes only (no device transfer). */
+int ndp_frontier_dims(const ndp_frontier* f, size_t k, size_t* n_clauses, size_t* n_choices);
+
+/* Build a frontier from host data: the -r resume path, replacing deserializeBFSResults
+ * (NDP:512-531).  clause_offsets/choice_offsets have count+1 entries (in clauses / in ints).
+ * DFS then runs on exactly these clause sets, as the reference's workers do (NDP:1422-1424). */
+int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets, const int32_t* choices,
+                           const size_t* choice_offsets, size_t count, ndp_frontier** out);
+
+void ndp_frontier_free(ndp_frontier* f);
+
+/* ---- DFS over the frontier --------------------------------------------------------------
+ * Replaces process_queue's dispatch loop + the per-task call at NDP:1424,
+ *   Satisfy_iterative(*clause_set, true)                             (definition NDP:784-878)
+ * for subproblems first, first+stride, first+2*stride, ... (< ndp_frontier_size): one rank's
+ * static interleaved shard (rank = first, world = stride); first=0,stride=1 is the whole
+ * frontier.  verdict[] has ndp_frontier_size entries indexed by GLOBAL subproblem index; only
+ * this shard's entries are written (others keep the caller's value).
+ *
+ * early_exit = 0: every subproblem of the shard is resolved (exhaustive).
+ * early_exit = 1: the reference's "first solution ends the job" (NDP:1297-1303, 1436-1447) made
+ *   deterministic: the winner is the LOWEST-index SAT subproblem; subproblems above a known
+ *   SAT index are abandoned (NDP_NOT_RUN).  *exit_flag (may be NULL) is an in/out hint shared
+ *   between shards: on entry the lowest SAT index known so far (or SIZE_MAX), on return the
+ *   lowest after this shard.
+ * winner: global index of the lowest SAT subproblem of this shard, or SIZE_MAX.
+ * model/model_len: choices_k ++ DFS choices of the winner -- final_choices_i of NDP:1430-1431;
+ *   model must hold model_cap ints.
+ * nodes/evals (may be NULL): per-subproblem counters, ndp_frontier_size entries each. */
+int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, size_t* exit_flag,
+                  uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                  uint64_t* nodes, uint64_t* evals, ndp_stats* stats);
+
+/* Whole frontier on n_gpus devices of this process (static interleaved split k -> k mod n_gpus,
+ * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1. */
+int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
+                  int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDP_B200_H */

@@ -1,0 +1,730 @@
+// ndp_engine.cu -- host side of the C ABI (include/ndp_b200.h): device arena, BFS level
+// driver with the reference's exact -d/-q stop rules, DFS launch, result gather.
+// There is no CPU fallback in this file: every compute entry point needs a CUDA device.
+#include "../../include/ndp_b200.h"
+#include "ndp_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace ndp;
+
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_device = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? NDP_E_NOMEM : NDP_E_CUDA,                      \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
+    } while (0)
+
+struct Entry {        // one frontier element
+    int buf;          // arena buffer holding its clause slot
+    uint32_t slot;
+    int32_t n;
+    int32_t tree;     // index into the choice tree (BFS frontiers) or -1
+};
+
+// What choice() (NDP-5_6_7.cpp:753-781) says about a host clause array: same encoding as SetInfo.
+void host_setinfo(const int32_t* c3, size_t n, int& kind, int& lit) {
+    if (n == 0) { kind = K_EMPTY; lit = 0; return; }
+    int lit2 = 0, lit1 = 0;
+    for (size_t k = 0; k < n && !lit2; ++k) {
+        int zc = 0, last = 0;
+        for (int j = 0; j < 3; ++j) { if (c3[3 * k + j] == 0) ++zc; else last = c3[3 * k + j]; }
+        if (zc == 2) lit2 = last;
+        else if (zc == 1 && !lit1) lit1 = last;
+    }
+    if (lit2) { kind = K_UNIT; lit = lit2; return; }
+    kind = K_DECIDE;
+    int v = lit1 ? lit1 : c3[0];
+    lit = v < 0 ? -v : v;
+}
+
+}  // namespace
+
+struct ndp_frontier {
+    int device = 0;
+    pclause* buf[2] = {nullptr, nullptr};   // the arena: two buffers of fixed-stride clause slots
+    size_t cap_slots[2] = {0, 0};
+    size_t stride = 0;                      // clauses per slot
+    int max_var = 0;
+    std::vector<Entry> entries;
+    // choices: either a parent-pointer tree (BFS) or flat arrays (resume)
+    std::vector<int32_t> tree_parent, tree_lit;
+    std::vector<int32_t> flat_choices;
+    std::vector<size_t> flat_off;
+    // BFS stats
+    uint64_t bfs_evals = 0, bfs_launches = 0;
+    double bfs_kernel_ms = 0;
+    // scratch for ndp_frontier_get
+    std::vector<int32_t> get_clauses, get_choices;
+    std::vector<pclause> get_packed;
+    // per-device DFS descriptors (built lazily): index = device ordinal position in `replicas`
+    struct Replica {
+        int device = -1;
+        size_t first = 0, stride = 1;        // the shard this replica serves
+        pclause* shard_buf = nullptr;        // private copy of the shard's slots (other devices only)
+        const pclause** d_base = nullptr;    // [n_local]
+        int32_t* d_n = nullptr;              // [n_local]
+        size_t n_local = 0;
+        int n_max = 0;
+    };
+    std::vector<Replica> replicas;
+
+    void choices_of(size_t k, std::vector<int32_t>& out) const {
+        out.clear();
+        const Entry& e = entries[k];
+        if (e.tree >= 0) {
+            for (int32_t t = e.tree; t > 0; t = tree_parent[t]) out.push_back(tree_lit[t]);
+            std::reverse(out.begin(), out.end());
+        } else if (!flat_off.empty()) {
+            out.assign(flat_choices.begin() + flat_off[k], flat_choices.begin() + flat_off[k + 1]);
+        }
+    }
+    size_t nchoices_of(size_t k) const {
+        const Entry& e = entries[k];
+        if (e.tree >= 0) {
+            size_t c = 0;
+            for (int32_t t = e.tree; t > 0; t = tree_parent[t]) ++c;
+            return c;
+        }
+        return flat_off.empty() ? 0 : flat_off[k + 1] - flat_off[k];
+    }
+    void free_replicas() {
+        for (auto& r : replicas) {
+            cudaSetDevice(r.device);
+            if (r.shard_buf) cudaFree(r.shard_buf);
+            if (r.d_base) cudaFree((void*)r.d_base);
+            if (r.d_n) cudaFree(r.d_n);
+        }
+        replicas.clear();
+    }
+    ~ndp_frontier() {
+        free_replicas();
+        cudaSetDevice(device);
+        for (int b = 0; b < 2; ++b)
+            if (buf[b]) cudaFree(buf[b]);
+    }
+};
+
+namespace {
+
+int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(NDP_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                    "); the NDP hot path has no CPU fallback");
+    if (g_device >= n) return fail(NDP_E_INVALID, "selected device does not exist");
+    CUDA_TRY(cudaSetDevice(g_device));
+    return NDP_OK;
+}
+
+int ensure_buf(ndp_frontier* f, int b, size_t slots) {
+    if (f->cap_slots[b] >= slots) return NDP_OK;
+    if (f->buf[b]) { CUDA_TRY(cudaFree(f->buf[b])); f->buf[b] = nullptr; f->cap_slots[b] = 0; }
+    size_t want = std::max(slots, (size_t)64);
+    CUDA_TRY(cudaMalloc(&f->buf[b], want * f->stride * sizeof(pclause)));
+    f->cap_slots[b] = want;
+    return NDP_OK;
+}
+
+// pack an int32 n x 3 clause array; returns false if a literal does not fit 16 bits
+bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
+    for (size_t k = 0; k < n; ++k) {
+        for (int j = 0; j < 3; ++j) {
+            int l = c3[3 * k + j];
+            if (l > kMaxLit || l < -kMaxLit) return false;
+            int v = l < 0 ? -l : l;
+            if (v > max_var) max_var = v;
+        }
+        out[k] = pack_clause(c3[3 * k], c3[3 * k + 1], c3[3 * k + 2]);
+    }
+    return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ndp_last_error(void) { return g_err.c_str(); }
+const char* ndp_version(void) { return "ndp-b200 0.1 (NDP 5.6.7 hot path, sm_100a)"; }
+
+int ndp_set_device(int device) {
+    if (device < 0) return fail(NDP_E_INVALID, "negative device ordinal");
+    g_device = device;
+    return NDP_OK;
+}
+int ndp_device_count(int* count) {
+    if (!count) return fail(NDP_E_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(NDP_E_CUDA, cudaGetErrorString(e)); }
+    *count = n;
+    return NDP_OK;
+}
+
+int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int override_max_iterations,
+            int max_queues, ndp_frontier** out, int* iterations_out, int* task_count_out,
+            size_t* initial_queue_size) {
+    if (!out) return fail(NDP_E_INVALID, "out is null");
+    *out = nullptr;
+    if (!clauses3 && n_clauses) return fail(NDP_E_INVALID, "clauses3 is null");
+    if (n_clauses > (size_t)INT_MAX / 4) return fail(NDP_E_UNSUPPORTED, "too many clauses");
+    int rc = check_device();
+    if (rc) return rc;
+
+    std::unique_ptr<ndp_frontier> f(new ndp_frontier);
+    f->device = g_device;
+    f->stride = std::max(n_clauses, (size_t)1);
+    std::vector<pclause> packed(f->stride);
+    if (!pack_host(clauses3, n_clauses, packed.data(), f->max_var))
+        return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32767 (16-bit clause packing)");
+    if ((rc = ensure_buf(f.get(), 0, 64))) return rc;
+    CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
+
+    struct HostNode { uint32_t slot; int32_t n, kind, lit, tree; };
+    std::vector<HostNode> cur, next;
+    {
+        HostNode r{0, (int32_t)n_clauses, 0, 0, 0};
+        host_setinfo(clauses3, n_clauses, r.kind, r.lit);
+        cur.push_back(r);
+    }
+    f->tree_parent.push_back(-1);
+    f->tree_lit.push_back(0);
+
+    const int D = max_iterations, Q = max_queues;
+    const bool ovr = override_max_iterations != 0;
+    long long it = 0, task_count = 1;
+    int cur_buf = 0;
+    BfsNode* d_nodes = nullptr;
+    BfsChild* d_children = nullptr;
+    size_t d_cap = 0;
+    std::vector<BfsNode> h_nodes;
+    std::vector<BfsChild> h_children;
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    int status = NDP_OK;
+    size_t E = 0;           // nodes of `cur` consumed when the loop stops
+    bool have_next = false; // `next` holds children that belong to the frontier
+
+    // Level-synchronous restatement of the FIFO loop NDP:893-937: a FIFO
+    // queue only ever holds the unexpanded rest of level L followed by the level-L+1 children
+    // pushed so far, so walking one level in order with the running queue size `s` reproduces
+    // every stop test at the exact pop it would fire.
+    for (;;) {
+        const size_t m = cur.size();
+        E = 0;
+        have_next = false;
+        if (m == 0) break;                                           // queue empty (NDP:893)
+        if (Q > 0 && m >= (size_t)Q) break;                          // NDP:894-895 before the level's first pop
+        if (D == -1 && !ovr) break;                                  // NDP:896-897 (iterations >= -1 always)
+        size_t need = m;
+        if (Q <= 0) {                                                // -d budget known in advance
+            long long R = (long long)D - it;
+            need = (size_t)std::min<long long>((long long)m, std::max<long long>(R, 1));
+        }
+        if ((status = ensure_buf(f.get(), cur_buf ^ 1, 2 * need))) break;
+        if (d_cap < need) {
+            if (d_nodes) cudaFree(d_nodes);
+            if (d_children) cudaFree(d_children);
+            d_cap = std::max(need * 2, (size_t)1024);
+            if (cudaMalloc(&d_nodes, d_cap * sizeof(BfsNode)) != cudaSuccess ||
+                cudaMalloc(&d_children, 2 * d_cap * sizeof(BfsChild)) != cudaSuccess) {
+                status = fail(NDP_E_NOMEM, "BFS level metadata allocation failed");
+                break;
+            }
+        }
+        h_nodes.resize(need);
+        for (size_t j = 0; j < need; ++j) h_nodes[j] = BfsNode{cur[j].slot, cur[j].n, cur[j].kind, cur[j].lit};
+        cudaMemcpyAsync(d_nodes, h_nodes.data(), need * sizeof(BfsNode), cudaMemcpyHostToDevice, 0);
+        const int warps_per_block = 8;
+        int grid = (int)std::min<size_t>((need + warps_per_block - 1) / warps_per_block, (size_t)148 * 16);
+        cudaEventRecord(ev0, 0);
+        bfs_expand_kernel<<<grid, warps_per_block * 32>>>(f->buf[cur_buf], f->buf[cur_buf ^ 1], f->stride, d_nodes,
+                                                          (int)need, d_children);
+        cudaEventRecord(ev1, 0);
+        h_children.resize(2 * need);
+        cudaError_t ce = cudaMemcpy(h_children.data(), d_children, 2 * need * sizeof(BfsChild), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS level: ") + cudaGetErrorString(ce)); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        f->bfs_kernel_ms += ms;
+        f->bfs_launches += 1;
+
+        next.clear();
+        size_t s = m;
+        bool stopped = false;
+        for (size_t j = 0; j < need; ++j) {
+            if (Q > 0 && s >= (size_t)Q) { stopped = true; break; }  // NDP:894-895 before this pop
+            const HostNode& nd = cur[j];
+            const int var = nd.kind == K_UNIT ? std::abs(nd.lit) : nd.lit;
+            E = j + 1;                                               // popped (NDP:898-899)
+            s -= 1;
+            if (nd.n == 0 || var == 0) continue;                     // choice()==0: `continue`, no iteration (NDP:901-902)
+            f->bfs_evals += (uint64_t)nd.n;
+            for (int b = 0; b < 2; ++b) {                            // LA then RA (NDP:904-925)
+                const BfsChild& c = h_children[2 * j + b];
+                if (c.n < 0) continue;
+                int32_t tree = (int32_t)f->tree_parent.size();
+                f->tree_parent.push_back(nd.tree);
+                f->tree_lit.push_back(b == 0 ? var : -var);
+                next.push_back(HostNode{(uint32_t)(2 * j + b), c.n, c.kind, c.lit, tree});
+                ++task_count;
+                ++s;
+            }
+            ++it;                                                    // NDP:926
+            if (Q <= 0 && it >= D) { stopped = true; break; }        // NDP:935-936
+        }
+        have_next = true;
+        if (stopped || E < m) break;
+        cur.swap(next);
+        cur_buf ^= 1;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (d_nodes) cudaFree(d_nodes);
+    if (d_children) cudaFree(d_children);
+    if (status) return status;
+
+    // frontier = unexpanded rest of the current level, then the children pushed so far
+    for (size_t j = E; j < cur.size(); ++j) f->entries.push_back(Entry{cur_buf, cur[j].slot, cur[j].n, cur[j].tree});
+    if (have_next)
+        for (const HostNode& c : next) f->entries.push_back(Entry{cur_buf ^ 1, c.slot, c.n, c.tree});
+
+    if (iterations_out) *iterations_out = (int)it;
+    if (task_count_out) *task_count_out = (int)task_count;
+    if (initial_queue_size && *initial_queue_size == 0) *initial_queue_size = f->entries.size();  // NDP:939-941
+    *out = f.release();
+    return NDP_OK;
+}
+
+int ndp_frontier_bfs_stats(const ndp_frontier* f, uint64_t* clause_evals, double* kernel_ms, uint64_t* launches) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (clause_evals) *clause_evals = f->bfs_evals;
+    if (kernel_ms) *kernel_ms = f->bfs_kernel_ms;
+    if (launches) *launches = f->bfs_launches;
+    return NDP_OK;
+}
+
+size_t ndp_frontier_size(const ndp_frontier* f) { return f ? f->entries.size() : 0; }
+
+int ndp_frontier_dims(const ndp_frontier* f, size_t k, size_t* n_clauses, size_t* n_choices) {
+    if (!f || k >= f->entries.size()) return fail(NDP_E_INVALID, "frontier index out of range");
+    if (n_clauses) *n_clauses = (size_t)f->entries[k].n;
+    if (n_choices) *n_choices = f->nchoices_of(k);
+    return NDP_OK;
+}
+
+int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t* n_clauses,
+                     const int32_t** choices, size_t* n_choices) {
+    if (!f || k >= f->entries.size()) return fail(NDP_E_INVALID, "frontier index out of range");
+    const Entry& e = f->entries[k];
+    if (clauses3 || n_clauses) {
+        CUDA_TRY(cudaSetDevice(f->device));
+        f->get_packed.resize((size_t)std::max(e.n, 1));
+        CUDA_TRY(cudaMemcpy(f->get_packed.data(), f->buf[e.buf] + (size_t)e.slot * f->stride,
+                            (size_t)e.n * sizeof(pclause), cudaMemcpyDeviceToHost));
+        f->get_clauses.resize((size_t)e.n * 3 + 1);
+        for (int32_t c = 0; c < e.n; ++c) {
+            const pclause p = f->get_packed[c];
+            f->get_clauses[3 * c] = sext16(p.x & 0xffffu);
+            f->get_clauses[3 * c + 1] = sext16(p.x >> 16);
+            f->get_clauses[3 * c + 2] = sext16(p.y & 0xffffu);
+        }
+        if (clauses3) *clauses3 = f->get_clauses.data();
+        if (n_clauses) *n_clauses = (size_t)e.n;
+    }
+    if (choices || n_choices) {
+        f->choices_of(k, f->get_choices);
+        if (f->get_choices.empty()) f->get_choices.reserve(1);
+        if (choices) *choices = f->get_choices.data();
+        if (n_choices) *n_choices = f->get_choices.size();
+    }
+    return NDP_OK;
+}
+
+int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets, const int32_t* choices,
+                           const size_t* choice_offsets, size_t count, ndp_frontier** out) {
+    if (!out) return fail(NDP_E_INVALID, "out is null");
+    *out = nullptr;
+    if (count && (!clause_offsets || !choice_offsets)) return fail(NDP_E_INVALID, "offset arrays are null");
+    int rc = check_device();
+    if (rc) return rc;
+    std::unique_ptr<ndp_frontier> f(new ndp_frontier);
+    f->device = g_device;
+    size_t stride = 1;
+    for (size_t k = 0; k < count; ++k) {
+        if (clause_offsets[k + 1] < clause_offsets[k] || choice_offsets[k + 1] < choice_offsets[k])
+            return fail(NDP_E_INVALID, "offset arrays must be non-decreasing");
+        stride = std::max(stride, clause_offsets[k + 1] - clause_offsets[k]);
+    }
+    if (stride > (size_t)INT_MAX / 4) return fail(NDP_E_UNSUPPORTED, "clause set too large");
+    f->stride = stride;
+    if ((rc = ensure_buf(f.get(), 0, std::max(count, (size_t)1)))) return rc;
+    // stage in bounded chunks so a multi-GB resume does not double its footprint on the host
+    const size_t chunk_slots = std::max<size_t>(1, ((size_t)64 << 20) / (stride * sizeof(pclause)));
+    std::vector<pclause> stage(chunk_slots * stride);
+    for (size_t k0 = 0; k0 < count; k0 += chunk_slots) {
+        size_t k1 = std::min(count, k0 + chunk_slots);
+        for (size_t k = k0; k < k1; ++k) {
+            size_t n = clause_offsets[k + 1] - clause_offsets[k];
+            if (!pack_host(clauses3 + 3 * clause_offsets[k], n, stage.data() + (k - k0) * stride, f->max_var))
+                return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32767 (16-bit clause packing)");
+            f->entries.push_back(Entry{0, (uint32_t)k, (int32_t)n, -1});
+        }
+        CUDA_TRY(cudaMemcpy(f->buf[0] + k0 * stride, stage.data(), (k1 - k0) * stride * sizeof(pclause),
+                            cudaMemcpyHostToDevice));
+    }
+    f->flat_off.assign(choice_offsets, choice_offsets + count + 1);
+    size_t base = count ? choice_offsets[0] : 0;
+    for (auto& o : f->flat_off) o -= base;
+    if (count) f->flat_choices.assign(choices + choice_offsets[0], choices + choice_offsets[count]);
+    if (count == 0) f->flat_off.assign(1, 0);
+    for (int32_t l : f->flat_choices) f->max_var = std::max(f->max_var, std::abs(l));
+    *out = f.release();
+    return NDP_OK;
+}
+
+void ndp_frontier_free(ndp_frontier* f) { delete f; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DfsLaunchPlan {
+    bool smem_w;
+    int warps_per_cta, ctas_per_sm, grid, smem_bytes;
+    DfsParams p;
+};
+
+// shared-memory layout of one warp and the launch shape that maximises resident warps
+int plan_dfs(int device, int n_max, int max_var, DfsLaunchPlan& plan) {
+    int sms = 0, smem_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    DfsParams& p = plan.p;
+    p.w_cap = std::max(n_max, 1);
+    p.trail_cap = std::max(max_var, 1);
+    p.table_words = (max_var + 1 + 15) / 16;
+    p.pend_words = (p.trail_cap + 31) / 32;
+    const size_t aux = align16((size_t)p.trail_cap * 2) + align16((size_t)p.table_words * 4) + align16((size_t)p.pend_words * 4);
+    const size_t w_bytes = align16((size_t)p.w_cap * sizeof(pclause));
+    plan.smem_w = w_bytes + aux <= (size_t)smem_optin;
+    const size_t per_warp = (plan.smem_w ? w_bytes : 0) + aux;
+    if (per_warp > (size_t)smem_optin)
+        return fail(NDP_E_UNSUPPORTED, "variable count too large for the shared-memory trail");
+    size_t off = plan.smem_w ? w_bytes : 0;
+    p.off_trail = (int)off; off += align16((size_t)p.trail_cap * 2);
+    p.off_table = (int)off; off += align16((size_t)p.table_words * 4);
+    p.off_pend = (int)off;  off += align16((size_t)p.pend_words * 4);
+    p.warp_bytes = (int)per_warp;
+    // pick warps/CTA in {8,6,4,3,2,1} maximising resident warps per SM (<= 32 to keep registers free)
+    int best_total = 0, best_w = 1, best_ctas = 1;
+    const int sm_smem = 233472 - 1024;  // 228 KB per SM, 1 KB reserved per resident CTA
+    for (int w : {8, 6, 4, 3, 2, 1}) {
+        size_t cta = per_warp * w;
+        if (cta > (size_t)smem_optin) continue;
+        int ctas = (int)std::min<size_t>(32, (size_t)sm_smem / (cta + 1024));
+        ctas = std::min(ctas, 32 / w);
+        if (ctas < 1) continue;
+        if (w * ctas > best_total) { best_total = w * ctas; best_w = w; best_ctas = ctas; }
+    }
+    plan.warps_per_cta = best_w;
+    plan.ctas_per_sm = best_ctas;
+    plan.smem_bytes = (int)(per_warp * best_w);
+    plan.grid = sms * best_ctas;
+    return NDP_OK;
+}
+
+int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_frontier::Replica** out) {
+    for (auto& r : f->replicas)
+        if (r.device == device && r.first == first && r.stride == stride) { *out = &r; return NDP_OK; }
+    ndp_frontier::Replica r;
+    r.device = device;
+    r.first = first;
+    r.stride = stride;
+    const size_t total = f->entries.size();
+    r.n_local = first < total ? (total - first + stride - 1) / stride : 0;
+    CUDA_TRY(cudaSetDevice(device));
+    std::vector<const pclause*> h_base(std::max(r.n_local, (size_t)1));
+    std::vector<int32_t> h_n(std::max(r.n_local, (size_t)1));
+    if (device != f->device && r.n_local) {
+        // private copy of this shard's slots on the other GPU, one peer copy per slot
+        CUDA_TRY(cudaMalloc(&r.shard_buf, r.n_local * f->stride * sizeof(pclause)));
+        for (size_t q = 0; q < r.n_local; ++q) {
+            const Entry& e = f->entries[first + q * stride];
+            CUDA_TRY(cudaMemcpyPeerAsync(r.shard_buf + q * f->stride, device,
+                                         f->buf[e.buf] + (size_t)e.slot * f->stride, f->device,
+                                         (size_t)e.n * sizeof(pclause), 0));
+        }
+        CUDA_TRY(cudaStreamSynchronize(0));
+    }
+    for (size_t q = 0; q < r.n_local; ++q) {
+        const Entry& e = f->entries[first + q * stride];
+        h_base[q] = r.shard_buf ? r.shard_buf + q * f->stride : f->buf[e.buf] + (size_t)e.slot * f->stride;
+        h_n[q] = e.n;
+        r.n_max = std::max(r.n_max, e.n);
+    }
+    CUDA_TRY(cudaMalloc((void**)&r.d_base, h_base.size() * sizeof(pclause*)));
+    CUDA_TRY(cudaMalloc(&r.d_n, h_n.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy((void*)r.d_base, h_base.data(), h_base.size() * sizeof(pclause*), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_n, h_n.data(), h_n.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    f->replicas.push_back(r);
+    *out = &f->replicas.back();
+    return NDP_OK;
+}
+
+struct DevBuf {  // tiny RAII for the per-call device outputs
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+// One shard on one device.  `best_dev`/`peers`: early-exit words (this device's + peers').
+int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int early_exit,
+                  unsigned long long* shared_best, unsigned long long* const* peer_best, int n_peers,
+                  unsigned long long best_init, uint8_t* verdict, size_t* winner, std::vector<int32_t>* model,
+                  uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
+    ndp_frontier::Replica* rep = nullptr;
+    int rc = build_replica(f, device, first, stride, &rep);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t nl = rep->n_local;
+    if (winner) *winner = SIZE_MAX;
+    if (nl == 0) return NDP_OK;
+    if (nl > 0xfffffff0ull) return fail(NDP_E_UNSUPPORTED, "shard larger than the 32-bit work counter");
+
+    DfsLaunchPlan plan;
+    if ((rc = plan_dfs(device, rep->n_max, f->max_var, plan))) return rc;
+    DfsParams& p = plan.p;
+    const int n_warps = plan.grid * plan.warps_per_cta;
+    p.model_stride = p.trail_cap;
+
+    DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_msub, b_mlen, b_models, b_scratch;
+    CUDA_TRY(cudaMalloc(&b_verdict.p, nl));
+    CUDA_TRY(cudaMalloc(&b_nodes.p, nl * 8));
+    CUDA_TRY(cudaMalloc(&b_evals.p, nl * 8));
+    CUDA_TRY(cudaMalloc(&b_reb.p, nl * 4));
+    CUDA_TRY(cudaMalloc(&b_next.p, 4));
+    CUDA_TRY(cudaMalloc(&b_msub.p, (size_t)n_warps * 8));
+    CUDA_TRY(cudaMalloc(&b_mlen.p, (size_t)n_warps * 4));
+    CUDA_TRY(cudaMalloc(&b_models.p, (size_t)n_warps * p.model_stride * 4));
+    if (!plan.smem_w) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * p.w_cap * sizeof(pclause)));
+    unsigned long long* d_best = shared_best;
+    if (!d_best) {
+        CUDA_TRY(cudaMalloc(&b_best.p, 8));
+        d_best = b_best.as<unsigned long long>();
+        CUDA_TRY(cudaMemcpy(d_best, &best_init, 8, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemset(b_verdict.p, NDP_NOT_RUN, nl));
+    CUDA_TRY(cudaMemset(b_next.p, 0, 4));
+    CUDA_TRY(cudaMemset(b_msub.p, 0xff, (size_t)n_warps * 8));
+
+    p.sub_base = rep->d_base;
+    p.sub_n = rep->d_n;
+    p.first = first; p.stride = stride; p.n_local = nl;
+    p.next = b_next.as<unsigned int>();
+    p.best = d_best;
+    p.n_peers = 0;
+    for (int d = 0; d < n_peers && d < 8; ++d)
+        if (peer_best[d] != d_best) p.peer_best[p.n_peers++] = peer_best[d];
+    p.early_exit = early_exit;
+    p.verdict = b_verdict.as<uint8_t>();
+    p.nodes = b_nodes.as<unsigned long long>();
+    p.evals = b_evals.as<unsigned long long>();
+    p.rebuilds = b_reb.as<unsigned int>();
+    p.model_sub = b_msub.as<unsigned long long>();
+    p.model_len = b_mlen.as<int32_t>();
+    p.models = b_models.as<int32_t>();
+    p.gscratch = b_scratch.as<pclause>();
+
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    auto kern = plan.smem_w ? dfs_kernel<true> : dfs_kernel<false>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    CUDA_TRY(cudaEventRecord(ev0, 0));
+    kern<<<plan.grid, plan.warps_per_cta * 32, plan.smem_bytes>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev1, 0));
+    CUDA_TRY(cudaEventSynchronize(ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+
+    std::vector<uint8_t> h_v(nl);
+    std::vector<unsigned long long> h_nodes(nl), h_evals(nl);
+    std::vector<unsigned> h_reb(nl);
+    CUDA_TRY(cudaMemcpy(h_v.data(), b_verdict.p, nl, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h_nodes.data(), b_nodes.p, nl * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h_evals.data(), b_evals.p, nl * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h_reb.data(), b_reb.p, nl * 4, cudaMemcpyDeviceToHost));
+    size_t win = SIZE_MAX;
+    uint64_t tn = 0, te = 0, tr = 0;
+    for (size_t q = 0; q < nl; ++q) {
+        const size_t g = first + q * stride;
+        if (verdict) verdict[g] = h_v[q];
+        if (nodes) nodes[g] = h_nodes[q];
+        if (evals) evals[g] = h_evals[q];
+        tn += h_nodes[q]; te += h_evals[q]; tr += h_reb[q];
+        if (h_v[q] == NDP_SAT && win == SIZE_MAX) win = g;
+    }
+    if (winner) *winner = win;
+    if (win != SIZE_MAX && model) {
+        std::vector<unsigned long long> h_msub(n_warps);
+        std::vector<int32_t> h_mlen(n_warps);
+        CUDA_TRY(cudaMemcpy(h_msub.data(), b_msub.p, (size_t)n_warps * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_mlen.data(), b_mlen.p, (size_t)n_warps * 4, cudaMemcpyDeviceToHost));
+        model->clear();
+        for (int w = 0; w < n_warps; ++w)
+            if (h_msub[w] == (unsigned long long)win) {
+                f->choices_of(win, *model);                       // choices_k ++ dfs choices (NDP:1430-1431)
+                std::vector<int32_t> tail((size_t)h_mlen[w]);
+                CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * p.model_stride,
+                                    tail.size() * 4, cudaMemcpyDeviceToHost));
+                model->insert(model->end(), tail.begin(), tail.end());
+                break;
+            }
+    }
+    if (stats) {
+        stats->nodes += tn;
+        stats->clause_evals += te;
+        stats->rebuilds += tr;
+        stats->kernel_ms = std::max(stats->kernel_ms, (double)ms);
+        stats->launches += 1;
+    }
+    return NDP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, size_t* exit_flag,
+                  uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                  uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (stride == 0) return fail(NDP_E_INVALID, "stride must be >= 1");
+    int rc = check_device();
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (model_len) *model_len = 0;
+    unsigned long long best_init = ~0ull;
+    if (exit_flag && *exit_flag != SIZE_MAX) best_init = *exit_flag;
+    std::vector<int32_t> m;
+    size_t win = SIZE_MAX;
+    rc = dfs_on_device(f, f->device, first, stride, early_exit, nullptr, nullptr, 0, best_init, verdict, &win,
+                       &m, nodes, evals, stats);
+    if (rc) return rc;
+    if (winner) *winner = win;
+    if (win != SIZE_MAX) {
+        if (exit_flag && (*exit_flag == SIZE_MAX || win < *exit_flag)) *exit_flag = win;
+        if (model_len) *model_len = m.size();
+        if (model) {
+            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, m.data(), m.size() * sizeof(int32_t));
+        }
+    }
+    return NDP_OK;
+}
+
+int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
+                  int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (n_gpus <= 1)
+        return ndp_dfs_shard(f, 0, 1, early_exit, nullptr, verdict, winner, model, model_cap, model_len, nullptr,
+                             nullptr, stats);
+    int have = 0;
+    int rc = ndp_device_count(&have);
+    if (rc) return rc;
+    if (n_gpus > have) return fail(NDP_E_INVALID, "n_gpus exceeds the devices visible to this process");
+    if (n_gpus > 8) return fail(NDP_E_UNSUPPORTED, "at most 8 devices per process");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (model_len) *model_len = 0;
+    if (winner) *winner = SIZE_MAX;
+    // devices: the frontier's home device first, then the others in ordinal order
+    std::vector<int> devs{f->device};
+    for (int d = 0; d < have && (int)devs.size() < n_gpus; ++d)
+        if (d != f->device) devs.push_back(d);
+    // peer-visible early-exit words: one per device, every kernel atomically lowers all of them
+    std::vector<unsigned long long*> best(n_gpus, nullptr);
+    const unsigned long long none = ~0ull;
+    for (int i = 0; i < n_gpus; ++i) {
+        CUDA_TRY(cudaSetDevice(devs[i]));
+        for (int j = 0; j < n_gpus; ++j)
+            if (i != j) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devs[i], devs[j]);
+                if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0); if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); }
+            }
+        CUDA_TRY(cudaMalloc(&best[i], 8));
+        CUDA_TRY(cudaMemcpy(best[i], &none, 8, cudaMemcpyHostToDevice));
+    }
+    // build replicas serially (peer copies from the home device), then search concurrently
+    for (int i = 0; i < n_gpus; ++i) {
+        ndp_frontier::Replica* rep = nullptr;
+        if ((rc = build_replica(f, devs[i], (size_t)i, (size_t)n_gpus, &rep))) return rc;
+    }
+    std::vector<int> rcs(n_gpus, 0);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<size_t> wins(n_gpus, SIZE_MAX);
+    std::vector<std::vector<int32_t>> models(n_gpus);
+    std::vector<ndp_stats> st(n_gpus);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_gpus; ++i)
+        th.emplace_back([&, i]() {
+            memset(&st[i], 0, sizeof(ndp_stats));
+            rcs[i] = dfs_on_device(f, devs[i], (size_t)i, (size_t)n_gpus, early_exit, best[i], best.data(), n_gpus,
+                                   none, verdict, &wins[i], &models[i], nullptr, nullptr, &st[i]);
+            if (rcs[i]) errs[i] = g_err;
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n_gpus; ++i) { cudaSetDevice(devs[i]); cudaFree(best[i]); }
+    cudaSetDevice(f->device);
+    for (int i = 0; i < n_gpus; ++i)
+        if (rcs[i]) return fail(rcs[i], errs[i]);
+    size_t win = SIZE_MAX;
+    int who = -1;
+    for (int i = 0; i < n_gpus; ++i)
+        if (wins[i] < win) { win = wins[i]; who = i; }
+    if (stats)
+        for (int i = 0; i < n_gpus; ++i) {
+            stats->nodes += st[i].nodes; stats->clause_evals += st[i].clause_evals; stats->rebuilds += st[i].rebuilds;
+            stats->kernel_ms = std::max(stats->kernel_ms, st[i].kernel_ms); stats->launches += st[i].launches;
+        }
+    if (winner) *winner = win;
+    if (who >= 0) {
+        if (model_len) *model_len = models[who].size();
+        if (model) {
+            if (models[who].size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, models[who].data(), models[who].size() * sizeof(int32_t));
+        }
+    }
+    return NDP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+"""ctypes binding of the product's C ABI (include/ndp_b200.h -> ndp-5_b200/lib/libndp_b200.so).
+
+This is plumbing for tests/, bench.py and __graft_entry__.py: it adds no logic of its own and
+never falls back to anything -- if the CUDA library is missing, import fails; if no B200 is
+present, every compute call raises NdpError(NDP_E_CUDA).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # ndp-5_b200/
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libndp_b200.so")
+HEADER_PATH = os.path.join(REPO_ROOT, "include", "ndp_b200.h")
+
+NDP_OK, NDP_E_INVALID, NDP_E_UNSUPPORTED, NDP_E_CUDA, NDP_E_NOMEM = range(5)
+UNSAT, SAT, NOT_RUN = 0, 1, 2
+SIZE_MAX = C.c_size_t(-1).value
+
+_i32p = C.POINTER(C.c_int32)
+_szp = C.POINTER(C.c_size_t)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class NdpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ndp_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("nodes", C.c_uint64), ("clause_evals", C.c_uint64), ("rebuilds", C.c_uint64),
+                ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    sig = {
+        "ndp_set_device": (C.c_int, [C.c_int]),
+        "ndp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+        "ndp_last_error": (C.c_char_p, []),
+        "ndp_version": (C.c_char_p, []),
+        "ndp_bfs": (C.c_int, [_i32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                              C.POINTER(C.c_int), C.POINTER(C.c_int), _szp]),
+        "ndp_frontier_bfs_stats": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_double), _u64p]),
+        "ndp_frontier_size": (C.c_size_t, [C.c_void_p]),
+        "ndp_frontier_get": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(_i32p), _szp, C.POINTER(_i32p), _szp]),
+        "ndp_frontier_dims": (C.c_int, [C.c_void_p, C.c_size_t, _szp, _szp]),
+        "ndp_frontier_from_host": (C.c_int, [_i32p, _szp, _i32p, _szp, C.c_size_t, C.POINTER(C.c_void_p)]),
+        "ndp_frontier_free": (None, [C.c_void_p]),
+        "ndp_dfs_shard": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, _szp, _u8p, _szp, _i32p,
+                                    C.c_size_t, _szp, _u64p, _u64p, C.POINTER(Stats)]),
+        "ndp_dfs_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u8p, _szp, _i32p, C.c_size_t, _szp,
+                                    C.POINTER(Stats)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc):
+    if rc != NDP_OK:
+        raise NdpError(rc, lib.ndp_last_error().decode(errors="replace"))
+
+
+def set_device(d):
+    _check(lib.ndp_set_device(int(d)))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib.ndp_device_count(C.byref(n))
+    return n.value if rc == NDP_OK else 0
+
+
+class Frontier:
+    """Owner of an ndp_frontier handle."""
+
+    def __init__(self, handle, iterations=0, task_count=0, initial_queue_size=0):
+        self.h = C.c_void_p(handle)
+        self.iterations = iterations
+        self.task_count = task_count
+        self.initial_queue_size = initial_queue_size
+
+    def __len__(self):
+        return int(lib.ndp_frontier_size(self.h))
+
+    def dims(self, k):
+        ncl, nch = C.c_size_t(0), C.c_size_t(0)
+        _check(lib.ndp_frontier_dims(self.h, k, C.byref(ncl), C.byref(nch)))
+        return ncl.value, nch.value
+
+    def get(self, k):
+        """(clauses [n,3] int32, choices [m] int32) of queue element k, copied out."""
+        cp, chp = _i32p(), _i32p()
+        ncl, nch = C.c_size_t(0), C.c_size_t(0)
+        _check(lib.ndp_frontier_get(self.h, k, C.byref(cp), C.byref(ncl), C.byref(chp), C.byref(nch)))
+        cl = np.ctypeslib.as_array(cp, shape=(ncl.value * 3,)).copy().reshape(-1, 3) if ncl.value else \
+            np.zeros((0, 3), np.int32)
+        ch = np.ctypeslib.as_array(chp, shape=(nch.value,)).copy() if nch.value else np.zeros(0, np.int32)
+        return cl, ch
+
+    def bfs_stats(self):
+        ev, ms, ln = C.c_uint64(0), C.c_double(0), C.c_uint64(0)
+        _check(lib.ndp_frontier_bfs_stats(self.h, C.byref(ev), C.byref(ms), C.byref(ln)))
+        return dict(clause_evals=ev.value, kernel_ms=ms.value, launches=ln.value)
+
+    def dfs_shard(self, first=0, stride=1, early_exit=False, exit_flag=None, model_cap=1 << 16, counters=True):
+        n = len(self)
+        verdict = np.full(max(n, 1), NOT_RUN, dtype=np.uint8)
+        nodes = np.zeros(max(n, 1), dtype=np.uint64)
+        evals = np.zeros(max(n, 1), dtype=np.uint64)
+        winner = C.c_size_t(SIZE_MAX)
+        flag = C.c_size_t(SIZE_MAX if exit_flag is None else exit_flag)
+        model = np.zeros(model_cap, dtype=np.int32)
+        mlen = C.c_size_t(0)
+        st = Stats()
+        _check(lib.ndp_dfs_shard(self.h, first, stride, int(early_exit), C.byref(flag),
+                                 verdict.ctypes.data_as(_u8p), C.byref(winner), model.ctypes.data_as(_i32p),
+                                 model_cap, C.byref(mlen),
+                                 nodes.ctypes.data_as(_u64p) if counters else None,
+                                 evals.ctypes.data_as(_u64p) if counters else None, C.byref(st)))
+        return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
+                    model=model[:mlen.value].copy(), nodes=nodes[:n], evals=evals[:n], stats=st.as_dict(),
+                    exit_flag=None if flag.value == SIZE_MAX else flag.value)
+
+    def dfs_batch(self, n_gpus=1, early_exit=False, model_cap=1 << 16):
+        n = len(self)
+        verdict = np.full(max(n, 1), NOT_RUN, dtype=np.uint8)
+        winner = C.c_size_t(SIZE_MAX)
+        model = np.zeros(model_cap, dtype=np.int32)
+        mlen = C.c_size_t(0)
+        st = Stats()
+        _check(lib.ndp_dfs_batch(self.h, int(n_gpus), int(early_exit), verdict.ctypes.data_as(_u8p),
+                                 C.byref(winner), model.ctypes.data_as(_i32p), model_cap, C.byref(mlen),
+                                 C.byref(st)))
+        return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
+                    model=model[:mlen.value].copy(), stats=st.as_dict())
+
+    def free(self):
+        if self.h:
+            lib.ndp_frontier_free(self.h)
+            self.h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def bfs(clauses, max_iterations, override_max_iterations, max_queues, initial_queue_size=0):
+    """ndp_bfs: same arguments as Satisfy_iterative_BFS (NDP-5_6_7.cpp:881-882)."""
+    a = np.ascontiguousarray(np.asarray(clauses, dtype=np.int32).reshape(-1, 3))
+    h = C.c_void_p(None)
+    it, tc = C.c_int(0), C.c_int(0)
+    iq = C.c_size_t(initial_queue_size)
+    _check(lib.ndp_bfs(a.ctypes.data_as(_i32p), a.shape[0], int(max_iterations), int(bool(override_max_iterations)),
+                       int(max_queues), C.byref(h), C.byref(it), C.byref(tc), C.byref(iq)))
+    return Frontier(h.value, it.value, tc.value, iq.value)
+
+
+def frontier_from_host(items):
+    """items: iterable of (clauses [n,3], choices [m]) -- the -r resume path."""
+    items = list(items)
+    cl_off, ch_off = [0], [0]
+    cls, chs = [], []
+    for cl, ch in items:
+        cl = np.asarray(cl, dtype=np.int32).reshape(-1, 3)
+        ch = np.asarray(ch, dtype=np.int32).reshape(-1)
+        cls.append(cl)
+        chs.append(ch)
+        cl_off.append(cl_off[-1] + cl.shape[0])
+        ch_off.append(ch_off[-1] + ch.shape[0])
+    cl_all = np.ascontiguousarray(np.concatenate(cls) if cls else np.zeros((0, 3), np.int32))
+    ch_all = np.ascontiguousarray(np.concatenate(chs) if chs else np.zeros(0, np.int32))
+    clo = np.asarray(cl_off, dtype=np.uintp)
+    cho = np.asarray(ch_off, dtype=np.uintp)
+    h = C.c_void_p(None)
+    _check(lib.ndp_frontier_from_host(cl_all.ctypes.data_as(_i32p), clo.ctypes.data_as(_szp),
+                                      ch_all.ctypes.data_as(_i32p), cho.ctypes.data_as(_szp), len(items),
+                                      C.byref(h)))
+    return Frontier(h.value)

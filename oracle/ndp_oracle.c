@@ -240,8 +240,16 @@ void orc_frontier_free(orc_frontier* f) {
 /* Satisfy_iterative -- NDP-5_6_7.cpp:784-878.  LIFO over materialised clause sets.  LA is
  * pushed before RA (NDP:837-842 then 857-862) so RA (i := false) is explored first; an empty
  * LA is a model immediately (NDP:843-852), checked before RA (NDP:863-872). */
+static uint64_t g_dfs_stats[8];
+/* design statistics of the last orc_dfs call (not part of the reference's behaviour):
+ * [0] nodes whose two children were both pushed, [1] nodes whose variable came from a
+ * two-zero (unit) clause, [2] max stack height, [3] sum of |LA| over pushed LA siblings of [0],
+ * [4] max |A| seen, [5] leaves (nodes that pushed nothing) */
+const uint64_t* orc_last_dfs_stats(void) { return g_dfs_stats; }
+
 int orc_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, size_t cap, size_t* model_len,
             uint64_t* nodes_out, uint64_t* clause_evals) {
+    memset(g_dfs_stats, 0, sizeof g_dfs_stats);
     size_t scap = 64, sp = 0;
     node_t* st = (node_t*)malloc(scap * sizeof(node_t));
     st[sp++] = node_make(c3, n, NULL, 0, 0, 0);                                /* NDP:793-795 */
@@ -277,6 +285,15 @@ int orc_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, s
         int cla, cra;
         orc_resolution_step(cur.cl, cur.n, i, 1, la, &nla, ra, &nra, &cla, &cra); /* NDP:831 */
         evals += cur.n;
+        {
+            int unit = 0;
+            for (size_t k = 0; k < cur.n && !unit; ++k) unit = abs_last_nonzero_if(cur.cl + 3 * k, 2) != 0;
+            g_dfs_stats[1] += (uint64_t)unit;
+            int open_la = nla && !cla, open_ra = nra && !cra;
+            if (open_la && open_ra) { ++g_dfs_stats[0]; g_dfs_stats[3] += nla; }
+            if (!open_la && !open_ra) ++g_dfs_stats[5];
+            if (cur.n > g_dfs_stats[4]) g_dfs_stats[4] = cur.n;
+        }
         int stop = 0;
         if (sp + 2 > scap) { scap *= 2; st = (node_t*)realloc(st, scap * sizeof(node_t)); }
         if (nla && !cla) {                                                     /* NDP:837-842 */
@@ -294,6 +311,7 @@ int orc_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, s
             }
         }
         node_free(&cur);
+        if (sp > g_dfs_stats[2]) g_dfs_stats[2] = sp;
         if (stop) break;
     }
 #undef RECORD_MODEL

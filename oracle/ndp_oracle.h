@@ -51,6 +51,9 @@ void orc_frontier_free(orc_frontier* f);
 int orc_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, size_t cap, size_t* model_len,
             uint64_t* nodes, uint64_t* clause_evals);
 
+/* design statistics of the last orc_dfs call; see ndp_oracle.c */
+const uint64_t* orc_last_dfs_stats(void);
+
 #ifdef __cplusplus
 }
 #endif

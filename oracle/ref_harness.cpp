@@ -146,21 +146,22 @@ int ref_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, s
 // first reported model.  verdict[k]: 0 UNSAT, 1 SAT, 2 not run.  Returns wall seconds.
 // winner/model: lowest-index SAT subproblem's full model = choices_k ++ dfs choices (NDP:1430-1431).
 double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int early_exit, uint8_t* verdict,
-                        long* winner, int32_t* model, size_t model_cap, size_t* model_len) {
+                        long* winner, int32_t* model, size_t model_cap, size_t* model_len, long* nodes_out) {
     Frontier& f = *static_cast<Frontier*>(h);
     if (first_k > f.size()) first_k = f.size();
     if (count > f.size() - first_k) count = f.size() - first_k;
     if (workers < 1) workers = 1;
     const size_t model_ints = 1u << 22;
     struct Shared { std::atomic<long> next; std::atomic<long> found; std::atomic<long> model_off; };
-    size_t bytes = sizeof(Shared) + count + model_ints * sizeof(int32_t) + count * sizeof(long) * 2;
+    size_t bytes = sizeof(Shared) + count + 64 + model_ints * sizeof(int32_t) + count * sizeof(long) * 3;
     char* mem = (char*)mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     Shared* sh = new (mem) Shared;
     sh->next = 0; sh->found = 0; sh->model_off = 0;
     uint8_t* v = (uint8_t*)(mem + sizeof(Shared));
     size_t voff = (sizeof(Shared) + count + 15) & ~size_t(15);
     long* moff = (long*)(mem + voff);            // per subproblem: offset, len into models
-    int32_t* models = (int32_t*)(mem + voff + count * sizeof(long) * 2);
+    long* ncount = moff + 2 * count;             // per subproblem: DFS loop iterations (prof build) or -1
+    int32_t* models = (int32_t*)(mem + voff + count * sizeof(long) * 3);
     memset(v, 2, count);
     double t0 = now_s();
     std::vector<pid_t> pids;
@@ -171,7 +172,9 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
                 if (early_exit && sh->found.load()) break;
                 long k = sh->next.fetch_add(1);
                 if (k >= (long)count) break;
+                long n_before = dfs_node_count();
                 auto res = Satisfy_iterative(f[first_k + k].first, true);
+                ncount[k] = n_before < 0 ? -1 : dfs_node_count() - n_before;
                 if (!res.empty()) {
                     const auto& ch = f[first_k + k].second;
                     long len = (long)(ch.size() + res[0].size());
@@ -206,6 +209,7 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
     long win = -1;
     for (size_t k = 0; k < count; ++k) if (v[k] == 1) { win = (long)k; break; }
     if (verdict) memcpy(verdict, v, count);
+    if (nodes_out) for (size_t k = 0; k < count; ++k) nodes_out[k] = v[k] == 2 ? 0 : ncount[k];
     if (winner) *winner = win < 0 ? -1 : (long)first_k + win;
     if (model_len) *model_len = 0;
     if (win >= 0 && moff[2 * win] >= 0) {

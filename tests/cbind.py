@@ -142,7 +142,8 @@ class RefLib(_Common):
                                               C.POINTER(C.c_long)])
         self._dfs_frontier = self._fn("dfs_frontier", C.c_double,
                                       [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
-                                       C.POINTER(C.c_uint8), C.POINTER(C.c_long), _i32p, C.c_size_t, _szp])
+                                       C.POINTER(C.c_uint8), C.POINTER(C.c_long), _i32p, C.c_size_t, _szp,
+                                       C.POINTER(C.c_long)])
         self._save = self._fn("save_bfs", C.c_size_t, [C.c_void_p] + [C.c_char_p] * 5 + [C.c_double, C.c_char_p,
                                                                                          C.c_size_t])
         self._read = self._fn("read_bfs", C.c_void_p, [C.c_char_p, C.POINTER(C.c_double)])
@@ -178,10 +179,13 @@ class RefLib(_Common):
         winner = C.c_long(-1)
         model = np.zeros(cap, dtype=np.int32)
         ml = C.c_size_t(0)
+        nodes = np.zeros(max(count, 1), dtype=np.int64)
         sec = self._dfs_frontier(handle, first_k, count, workers, int(early_exit),
                                  verdict.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(winner),
-                                 model.ctypes.data_as(_i32p), cap, C.byref(ml))
-        return dict(seconds=sec, verdict=verdict[:count].copy(), winner=winner.value, model=model[:ml.value].copy())
+                                 model.ctypes.data_as(_i32p), cap, C.byref(ml),
+                                 nodes.ctypes.data_as(C.POINTER(C.c_long)))
+        return dict(seconds=sec, verdict=verdict[:count].copy(), winner=winner.value, model=model[:ml.value].copy(),
+                    nodes=nodes[:count].copy())
 
     def save_bfs(self, handle, script, filename, pid, flag, outdir, bfs_time):
         buf = C.create_string_buffer(4096)

@@ -1,0 +1,296 @@
+"""Parity of the CUDA path (through the C ABI, include/ndp_b200.h) against the oracle and the
+golden vectors the unmodified reference produced.  Bar: bit-exact -- same BFS frontier in the
+same order (clause lists with their zeros, choices), same iterations/task_count, same
+SAT/UNSAT verdict per subproblem, same model, and (stronger than the reference's API needs)
+the same DFS node count and clause-evaluation count per subproblem."""
+import numpy as np
+import pytest
+
+import util_cnf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nd():
+    import ndp5_b200
+    assert ndp5_b200.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    return ndp5_b200
+
+
+def gpu_frontier_list(fr):
+    return [fr.get(k) for k in range(len(fr))]
+
+
+def check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, tag):
+    o = oracle.bfs(A, D, ovr, Q)
+    fr = nd.bfs(A, D, ovr, Q)
+    assert fr.iterations == o["iterations"], tag
+    assert fr.task_count == o["task_count"], tag
+    assert fr.initial_queue_size == o["initial_queue_size"], tag
+    assert len(fr) == o["size"], tag
+    got = gpu_frontier_list(fr)
+    for k, ((c1, h1), (c2, h2)) in enumerate(zip(got, o["frontier"])):
+        assert c1.shape == c2.shape and (c1 == c2).all(), (tag, k, "clauses")
+        assert h1.shape == h2.shape and (h1 == h2).all(), (tag, k, "choices")
+        assert fr.dims(k) == (c2.shape[0], h2.shape[0])
+    assert fr.bfs_stats()["clause_evals"] == o["clause_evals"], tag
+    return fr, o
+
+
+# ------------------------------------------------------------------------------------------ BFS
+def test_bfs_golden_all_cases(nd, oracle, golden, cnf_text):
+    """Every golden BFS case: counters, per-element sizes and the frontier digest."""
+    for c in golden["cases"]:
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        key = (c["cnf"], c["mode"], c["value"])
+        assert (fr.iterations, fr.task_count, fr.initial_queue_size, len(fr)) == \
+            (c["iterations"], c["task_count"], c["initial_queue_size"], c["size"]), key
+        assert [fr.dims(k) for k in range(len(fr))] == list(zip(c["nclauses"], c["nchoices"])), key
+        assert util_cnf.frontier_digest(gpu_frontier_list(fr)) == c["frontier_sha256"], key
+        assert fr.bfs_stats()["clause_evals"] == c["bfs_clause_evals"], key
+        fr.free()
+
+
+def test_bfs_random_small(nd, oracle):
+    """Random 3-CNFs with units, pre-zeroed literals, duplicates, tautologies; -d and -q sweeps
+    including the degenerate settings (-d -1, negative -d, -q 0/1)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        nv = int(rng.integers(2, 40))
+        A = util_cnf.random_cnf(rng, nv, int(rng.integers(1, 120)), p_unit=0.05, p_binary=0.15, p_dup=0.05,
+                                p_taut=0.05)
+        for mode, value in [("d", int(rng.integers(-3, 60))), ("q", int(rng.integers(-1, 20)))]:
+            D, ovr, Q = util_cnf.settings_for(mode, value)
+            fr, _ = check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, (trial, mode, value))
+            fr.free()
+
+
+def test_bfs_edge_cases(nd, oracle):
+    unit_only = np.array([[0, 0, 1], [0, 0, -2], [0, 0, 3]], dtype=np.int32)
+    contradictory = np.array([[0, 0, 1], [0, 0, -1]], dtype=np.int32)
+    one = np.array([[1, 2, 3]], dtype=np.int32)
+    all_zero_first = np.array([[0, 0, 0], [1, 2, 3]], dtype=np.int32)
+    all_zero_mid = np.array([[0, 0, 4], [0, 0, 0], [1, 2, 3]], dtype=np.int32)
+    sparse_ids = np.array([[30000, -32767, 5], [0, 0, -30000], [0, 32767, 7]], dtype=np.int32)
+    for name, A in [("unit_only", unit_only), ("contradictory", contradictory), ("one", one),
+                    ("all_zero_first", all_zero_first), ("all_zero_mid", all_zero_mid), ("sparse_ids", sparse_ids)]:
+        for D, ovr, Q in [(-1, False, -1), (1, False, -1), (5, False, -1), (100, False, -1), (0, True, 1),
+                          (0, True, 2), (0, True, 100), (0, False, -1), (-7, False, -1), (0, True, 0)]:
+            fr, _ = check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, (name, D, ovr, Q))
+            fr.free()
+
+
+def test_unsupported_literal_width_fails_loudly(nd):
+    with pytest.raises(nd.NdpError) as ei:
+        nd.bfs(np.array([[1, 2, 40000]], dtype=np.int32), 1, False, -1)
+    assert ei.value.code == nd.NDP_E_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------ DFS
+def check_dfs_against_oracle(nd, oracle, fr, ofr, tag):
+    r = fr.dfs_shard()
+    first_sat = None
+    for k, (cl, ch) in enumerate(ofr):
+        od = oracle.dfs(cl)
+        assert int(r["verdict"][k]) == (1 if od["models"] else 0), (tag, k, "verdict")
+        assert int(r["nodes"][k]) == od["nodes"], (tag, k, "nodes")
+        assert int(r["evals"][k]) == od["clause_evals"], (tag, k, "clause_evals")
+        if od["models"] and first_sat is None:
+            first_sat = (k, np.concatenate([ch, od["model"]]))
+    if first_sat is None:
+        assert r["winner"] is None and r["model"].size == 0, tag
+    else:
+        assert r["winner"] == first_sat[0], tag
+        assert r["model"].tolist() == first_sat[1].tolist(), tag
+    return r
+
+
+def test_dfs_golden_small_and_medium(nd, oracle, golden, cnf_text):
+    """Golden DFS cases up to 24-bit: verdict vector, node counts, clause evals, every SAT
+    subproblem's model (by making it the winner through a one-element shard)."""
+    n = 0
+    for c in golden["cases"]:
+        if "verdict" not in c or c["bits"] > 24:
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        r = fr.dfs_shard()
+        key = (c["cnf"], c["mode"], c["value"])
+        assert r["verdict"].tolist() == c["verdict"], key
+        assert r["nodes"].tolist() == c["nodes"], key
+        assert r["evals"].tolist() == c["clause_evals"], key
+        assert r["stats"]["nodes"] == sum(c["nodes"]) and r["stats"]["clause_evals"] == sum(c["clause_evals"]), key
+        if c["winner"] >= 0:
+            assert r["winner"] == c["winner"], key
+            assert r["model"].tolist() == c["sat"][str(c["winner"])]["model"], key
+        else:
+            assert r["winner"] is None, key
+        for k, s in c["sat"].items():   # every SAT element, not just the winner
+            rk = fr.dfs_shard(first=int(k), stride=len(fr) + 1)
+            assert rk["winner"] == int(k) and rk["model"].tolist() == s["model"], (key, k)
+            assert util_cnf.satisfies(A, rk["model"]), (key, k)
+        fr.free()
+        n += 1
+    assert n >= 15
+
+
+def test_dfs_random_small(nd, oracle):
+    rng = np.random.default_rng(99)
+    sat = 0
+    for trial in range(60):
+        nv = int(rng.integers(2, 40))
+        A = util_cnf.random_cnf(rng, nv, int(rng.integers(1, 150)), p_unit=0.03, p_binary=0.12, p_dup=0.04,
+                                p_taut=0.04)
+        D, ovr, Q = util_cnf.settings_for("q", int(rng.integers(1, 12)))
+        fr, o = check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, ("dfs-random", trial))
+        r = check_dfs_against_oracle(nd, oracle, fr, o["frontier"], ("dfs-random", trial))
+        sat += int((r["verdict"] == 1).sum())
+        if r["winner"] is not None:
+            assert util_cnf.satisfies(A, r["model"])
+        fr.free()
+    assert sat > 0
+
+
+def test_dfs_edge_cases_through_resume_path(nd, oracle):
+    """ndp_frontier_from_host (the -r path) with hand-made subproblems: empty set (model = its
+    choices), a set whose first clause is {0,0,0} (the reference's choice()==0 quirk), unit-only,
+    contradictory units, duplicates, a ragged mix of sizes."""
+    items = [
+        (np.zeros((0, 3), np.int32), np.array([5, -6], np.int32)),
+        (np.array([[0, 0, 0], [1, 2, 3]], np.int32), np.array([9], np.int32)),
+        (np.array([[0, 0, 1], [0, 0, -2], [0, 0, 3]], np.int32), np.zeros(0, np.int32)),
+        (np.array([[0, 0, 1], [0, 0, -1]], np.int32), np.array([4], np.int32)),
+        (np.array([[1, 1, 1], [-1, -1, -1]], np.int32), np.zeros(0, np.int32)),
+        (np.array([[1, 2, 3]], np.int32), np.array([-7, 8, 9], np.int32)),
+        (np.array([[0, 0, 4], [0, 0, 0], [1, 2, 3]], np.int32), np.zeros(0, np.int32)),
+        (np.array([[1, -2, 3], [-1, 2, 0], [0, -3, 2], [1, 2, 3], [-1, -2, -3]], np.int32), np.array([11], np.int32)),
+    ]
+    fr = nd.frontier_from_host(items)
+    assert len(fr) == len(items)
+    for k, (cl, ch) in enumerate(items):
+        c2, h2 = fr.get(k)
+        assert (c2 == cl).all() and (h2 == ch).all()
+    r = fr.dfs_shard()
+    for k, (cl, ch) in enumerate(items):
+        od = oracle.dfs(cl)
+        assert int(r["verdict"][k]) == (1 if od["models"] else 0), k
+        assert int(r["nodes"][k]) == od["nodes"] and int(r["evals"][k]) == od["clause_evals"], k
+        rk = fr.dfs_shard(first=k, stride=len(items) + 1)
+        if od["models"]:
+            assert rk["winner"] == k and rk["model"].tolist() == np.concatenate([ch, od["model"]]).tolist(), k
+        else:
+            assert rk["winner"] is None
+    fr.free()
+    empty = nd.frontier_from_host([])
+    assert len(empty) == 0
+    r = empty.dfs_shard()
+    assert r["winner"] is None and r["verdict"].size == 0
+
+
+def test_resume_equals_straight_run(nd, oracle, cnf_text):
+    """-s / -r round trip at the ABI: a frontier rebuilt from its own exported elements gives the
+    same verdicts, counters and model (BASELINE config 5's save/resume requirement)."""
+    for name, q in [("prime-16bit", 64), ("rsaFACT-16bit", 32)]:
+        A = oracle.parse(cnf_text(name))
+        fr = nd.bfs(A, 0, True, q)
+        r1 = fr.dfs_shard()
+        fr2 = nd.frontier_from_host(gpu_frontier_list(fr))
+        r2 = fr2.dfs_shard()
+        assert r1["verdict"].tolist() == r2["verdict"].tolist()
+        assert r1["nodes"].tolist() == r2["nodes"].tolist() and r1["evals"].tolist() == r2["evals"].tolist()
+        assert r1["winner"] == r2["winner"] and r1["model"].tolist() == r2["model"].tolist()
+        fr.free()
+        fr2.free()
+
+
+def test_sharding_does_not_change_answers(nd, oracle, cnf_text):
+    """Static interleaved shards k -> k mod G (G = 1,2,4,8) reproduce the single-shard verdict
+    vector; the global winner is the minimum over shards."""
+    A = oracle.parse(cnf_text("rsaFACT-16bit"))
+    fr = nd.bfs(A, 2240, False, -1)
+    full = fr.dfs_shard()
+    for G in (2, 4, 8):
+        verdict = np.full(len(fr), 2, np.uint8)
+        winners = []
+        for rank in range(G):
+            r = fr.dfs_shard(first=rank, stride=G)
+            mine = np.arange(rank, len(fr), G)
+            verdict[mine] = r["verdict"][mine]
+            assert (r["verdict"][np.setdiff1d(np.arange(len(fr)), mine)] == 2).all()
+            if r["winner"] is not None:
+                winners.append((r["winner"], r["model"].tolist()))
+        assert verdict.tolist() == full["verdict"].tolist()
+        assert min(winners)[0] == full["winner"] and min(winners)[1] == full["model"].tolist()
+    fr.free()
+
+
+def test_early_exit_is_deterministic(nd, oracle, golden, cnf_text):
+    """early_exit=1: the winner is the lowest-index SAT subproblem and its model is the
+    exhaustive run's; everything at or below the winner is resolved, nothing above it is SAT
+    with a lower index."""
+    for c in golden["cases"]:
+        if "verdict" not in c or c["winner"] < 0 or c["bits"] > 24:
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        for _ in range(3):
+            r = fr.dfs_shard(early_exit=True)
+            w = c["winner"]
+            assert r["winner"] == w and r["model"].tolist() == c["sat"][str(w)]["model"]
+            assert r["verdict"][: w + 1].tolist() == c["verdict"][: w + 1]
+            assert r["exit_flag"] == w
+        fr.free()
+
+
+# ------------------------------------------------------------------------------------ full size
+def test_full_size_32bit_q1024(nd, oracle, golden, cnf_text):
+    """BASELINE configs[1]'s CNF at the bench's frontier width: 1024 subproblems, exhaustive.
+    Golden verdicts / node counts are the reference's; clause evals the oracle's.  Also the
+    size-independent properties: the model satisfies the ORIGINAL CNF and decodes to the factors."""
+    for name in ("rsaFACT-32bit", "prime-32bit"):
+        c = next(x for x in golden["cases"] if (x["cnf"], x["mode"], x["value"]) == (name, "q", 1024))
+        A = oracle.parse(cnf_text(name))
+        fr = nd.bfs(A, 0, True, 1024)
+        assert (fr.iterations, fr.task_count, len(fr)) == (c["iterations"], c["task_count"], 1024)
+        assert util_cnf.frontier_digest(gpu_frontier_list(fr)) == c["frontier_sha256"]
+        r = fr.dfs_shard()
+        assert r["verdict"].tolist() == c["verdict"]
+        assert r["nodes"].tolist() == c["nodes"]
+        assert r["evals"].tolist() == c["clause_evals"]
+        if c["winner"] >= 0:
+            assert r["winner"] == c["winner"]
+            s = c["sat"][str(c["winner"])]
+            assert r["model"].tolist() == s["model"]
+            assert util_cnf.satisfies(A, r["model"])
+            import re
+            text = cnf_text(name)
+            v1 = [int(x) for x in re.search(r"first input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+            v2 = [int(x) for x in re.search(r"second input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+            d1, d2 = util_cnf.decode_factors(r["model"], v1, v2)
+            assert d1 * d2 == int(c["N"]) and (str(d1), str(d2)) == (s["fact1"], s["fact2"])
+        else:
+            assert r["winner"] is None and not r["verdict"].any()
+        fr.free()
+
+
+def test_single_subproblem_32bit_d12(nd, oracle, golden, cnf_text):
+    """BASELINE configs[1] verbatim: -d 12 gives ONE subproblem (SURVEY.md finding 1); the DFS to
+    the first model is 3 713 280 reference loop iterations (SURVEY.md §8c KAT)."""
+    A = oracle.parse(cnf_text("rsaFACT-32bit"))
+    fr = nd.bfs(A, 12, False, -1)
+    assert len(fr) == 1 and fr.dims(0) == (5629, 12)
+    r = fr.dfs_shard(early_exit=True)
+    assert r["winner"] == 0 and int(r["nodes"][0]) == 3713280
+    assert util_cnf.satisfies(A, r["model"])
+    import re
+    text = cnf_text("rsaFACT-32bit")
+    v1 = [int(x) for x in re.search(r"first input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+    v2 = [int(x) for x in re.search(r"second input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+    d1, d2 = util_cnf.decode_factors(r["model"], v1, v2)
+    assert {d1, d2} == {45887, 54493}
+    fr.free()
