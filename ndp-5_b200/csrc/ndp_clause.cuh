@@ -1,27 +1,31 @@
-// ndp_clause.cuh -- packed clause representation and the warp-wide resolution pass.
+// ndp_clause.cuh -- packed clause representation and the warp-wide resolution passes.
 //
 // A clause is the reference's Clause3 (ClauseSetPool.hpp:37-39: three int literals, 0 = "already
-// false / padding") packed into 8 bytes: three int16 fields + one zero pad, so that one lane
-// moves one clause with a single 64-bit access and a warp moves 32 clauses (256 B) per
-// instruction.  Clause sets are dense arrays of these records ("slots" of a device arena).
+// false / padding") packed into 8 bytes so that one lane moves one clause with a single 64-bit
+// access and a warp moves 32 clauses (256 B) per instruction:
 //
-// warp_apply() is the device restatement of ResolutionStepWithConflict for ONE branch
-// (NDP-5_6_7.cpp:654-697): make literal t true => clauses holding t are satisfied and dropped,
-// occurrences of -t become 0, emission order is preserved (stable warp-scan compaction), and
-// an emitted {0,0,0} raises the branch's conflict flag.  The same pass also produces what the
-// next call of choice() (NDP-5_6_7.cpp:753-781) would return for the emitted set, by
-// tracking the first emitted clause with two zeros, the first with one zero, and the first
-// clause at all -- so the branching variable of the child is known without another scan.
+//     x = c0 | c1 << 16          y = c2 | zc << 16
+//
+// c_j is the 16-bit sign-magnitude CODE of literal l_j:  0 for literal 0, else (|l| << 1) | (l < 0).
+// With this code one XOR against code(t) answers both questions the resolution step asks of a
+// literal (NDP-5_6_7.cpp:671-680): result 0 => the literal IS t (clause satisfied), result 1 =>
+// the literal is -t (it becomes 0).  zc caches the clause's zero count, which is what choice()
+// (NDP-5_6_7.cpp:753-781) keys on.  A record with x == y == 0xffffffff is a TOMBSTONE: a clause
+// that was satisfied and dropped but not yet squeezed out (lazy deletion, DFS only).
+//
+// Clause sets are dense arrays of these records ("slots" of a device arena).  Stable order is
+// preserved everywhere, because choice() is first-in-order.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace ndp {
 
-typedef uint2 pclause;  // x = l0 | l1 << 16 ; y = l2 (upper half zero)
+typedef uint2 pclause;
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kMaxLit = 32767;
+constexpr int kMaxVar = 32766;   // code 0xfffe/0xffff (variable 32767) is reserved for tombstones
+constexpr unsigned kTomb = 0xffffffffu;
 
 enum : int { K_EMPTY = 0, K_UNIT = 1, K_DECIDE = 2 };
 
@@ -31,19 +35,31 @@ enum : int { K_EMPTY = 0, K_UNIT = 1, K_DECIDE = 2 };
 //  K_DECIDE: lit = the variable (>= 0) from the first one-zero clause's last literal
 //            (NDP:767-777) or |A[0].l[0]| (NDP:778-779); lit == 0 only when A[0] is {0,0,0}.
 struct SetInfo {
-    int n;         // clauses in the set
+    int n;         // live clauses in the set
     int conflict;  // some clause is {0,0,0}
     int kind;
     int lit;
 };
 
+__host__ __device__ __forceinline__ unsigned lit_code(int l) {
+    return l == 0 ? 0u : (((unsigned)(l < 0 ? -l : l)) << 1) | (l < 0 ? 1u : 0u);
+}
+__host__ __device__ __forceinline__ int code_lit(unsigned c) {
+    int v = (int)(c >> 1);
+    return (c & 1u) ? -v : v;
+}
 __host__ __device__ __forceinline__ pclause pack_clause(int l0, int l1, int l2) {
     pclause c;
-    c.x = ((unsigned)l0 & 0xffffu) | (((unsigned)l1 & 0xffffu) << 16);
-    c.y = ((unsigned)l2 & 0xffffu);
+    unsigned zc = (l0 == 0) + (l1 == 0) + (l2 == 0);
+    c.x = lit_code(l0) | (lit_code(l1) << 16);
+    c.y = lit_code(l2) | (zc << 16);
     return c;
 }
-__host__ __device__ __forceinline__ int sext16(unsigned f) { return (int)(short)(unsigned short)f; }
+__host__ __device__ __forceinline__ void unpack_clause(pclause c, int& l0, int& l1, int& l2) {
+    l0 = code_lit(c.x & 0xffffu);
+    l1 = code_lit(c.x >> 16);
+    l2 = code_lit(c.y & 0xffffu);
+}
 
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -51,26 +67,54 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// Running answer to "what would choice() return for the clauses emitted so far".
+// Per-lane resolution of one clause against "literal with code ct becomes true".
+// Returns true when the clause mentions the variable at all ("touched").
+//   sat  : the clause holds the true literal (dropped in this branch, NDP:671-673 / 674-676)
+//   else : occurrences of the false literal are zeroed and zc is bumped; x,y updated in place.
+__device__ __forceinline__ bool resolve_clause(unsigned& x, unsigned& y, unsigned t2, unsigned ct, bool& sat) {
+    const unsigned zx = x ^ t2, zy = y ^ ct;
+    const bool m0 = (zx & 0x0000fffeu) == 0u, m1 = (zx & 0xfffe0000u) == 0u, m2 = (zy & 0x0000fffeu) == 0u;
+    sat = false;
+    if (!(m0 | m1 | m2)) return false;
+    sat = (m0 && !(zx & 1u)) || (m1 && !(zx & 0x10000u)) || (m2 && !(zy & 1u));
+    if (!sat) {
+        if (m0) x &= 0xffff0000u;
+        if (m1) x &= 0x0000ffffu;
+        if (m2) y &= 0xffff0000u;
+        y += ((unsigned)m0 + (unsigned)m1 + (unsigned)m2) << 16;
+    }
+    return true;
+}
+// cheap "does this clause mention the variable" test for the streaming phase
+__device__ __forceinline__ bool touches(unsigned x, unsigned y, unsigned t2, unsigned ct) {
+    const unsigned vx = (x ^ t2) & 0xfffefffeu;
+    const unsigned hz = (vx - 0x00010001u) & ~vx & 0x80008000u;   // a zero halfword in vx
+    return (hz != 0u) | (((y ^ ct) & 0x0000fffeu) == 0u);
+}
+
+// Running answer to "what would choice() return for the live clauses seen so far".
 struct ChoiceTracker {
-    int lit2 = 0;        // literal of the first emitted two-zero clause (0 = none yet)
-    int lit1 = 0;        // last literal of the first emitted one-zero clause (0 = none yet)
-    int first = 0;       // l[0] of the first emitted clause
+    int lit2 = 0;        // literal of the first live two-zero clause (0 = none yet)
+    int lit1 = 0;        // last literal of the first live one-zero clause (0 = none yet)
+    int first = 0;       // l[0] of the first live clause
     bool have_first = false;
 
-    // f0,f1,f2: this lane's post-resolution fields; emit: lane emits; zc: its zero count.
-    __device__ __forceinline__ void update(unsigned emask, bool emit, int zc, unsigned f0, unsigned f1, unsigned f2) {
-        if (!have_first && emask) {
-            first = sext16(__shfl_sync(kFullMask, f0, __ffs(emask) - 1));
-            have_first = true;
+    // x,y: this lane's post-resolution record; live: the lane holds a live clause.
+    __device__ __forceinline__ void update(bool live, unsigned x, unsigned y) {
+        const unsigned zc = (y >> 16) & 3u;
+        if (!have_first) {
+            unsigned ma = __ballot_sync(kFullMask, live);
+            if (ma) { first = code_lit(__shfl_sync(kFullMask, x & 0xffffu, __ffs(ma) - 1)); have_first = true; }
         }
-        if (lit2 == 0) {
-            unsigned m2 = __ballot_sync(kFullMask, emit && zc == 2);
-            if (m2) {
-                lit2 = sext16(__shfl_sync(kFullMask, f0 | f1 | f2, __ffs(m2) - 1));
-            } else if (lit1 == 0) {
-                unsigned m1 = __ballot_sync(kFullMask, emit && zc == 1);
-                if (m1) lit1 = sext16(__shfl_sync(kFullMask, f2 ? f2 : f1, __ffs(m1) - 1));
+        unsigned m2 = __ballot_sync(kFullMask, live && zc == 2u);
+        if (m2) {
+            unsigned only = (x & 0xffffu) | (x >> 16) | (y & 0xffffu);
+            lit2 = code_lit(__shfl_sync(kFullMask, only, __ffs(m2) - 1));
+        } else if (lit1 == 0) {
+            unsigned m1 = __ballot_sync(kFullMask, live && zc == 1u);
+            if (m1) {
+                unsigned last = (y & 0xffffu) ? (y & 0xffffu) : (x >> 16);
+                lit1 = code_lit(__shfl_sync(kFullMask, last, __ffs(m1) - 1));
             }
         }
     }
@@ -81,43 +125,29 @@ struct ChoiceTracker {
     }
 };
 
-// One branch of the resolution step over src[0..n): literal t becomes true.
-//  kWrite: emit the surviving clauses to dst (dst may equal src: the compaction is stable and
-//          only ever writes at or below the position it has already read, so it is safe in
-//          place); without kWrite the pass only classifies the branch.
-// All 32 lanes must call it with identical arguments; the result is warp-uniform.
-template <bool kWrite, int kUnroll = 4>
-__device__ __forceinline__ SetInfo warp_apply(const pclause* src, int n, pclause* dst, int t, unsigned lane) {
-    const unsigned tu = (unsigned)t & 0xffffu;
-    const unsigned ntu = (unsigned)(-t) & 0xffffu;
+// ------------------------------------------------------------------------------------------
+// EAGER pass (BFS): one branch of the resolution step over src[0..n) written, stably compacted,
+// to dst (a different slot).  ResolutionStep + the conflict scan + the child's choice() in one
+// read of the parent (NDP-5_6_7.cpp:700-750, 905-907, 753-781).  src holds no tombstones.
+__device__ __forceinline__ SetInfo warp_apply_copy(const pclause* __restrict__ src, int n, pclause* __restrict__ dst,
+                                                   int t, unsigned lane) {
+    const unsigned ct = lit_code(t), t2 = ct | (ct << 16);
     const unsigned lt = lanemask_lt();
     ChoiceTracker trk;
     int out = 0;
     bool confl = false;
-    for (int base = 0; base < n; base += 32 * kUnroll) {
-        pclause c[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            int idx = base + u * 32 + (int)lane;
-            c[u] = idx < n ? src[idx] : make_uint2(tu, 0u);  // padding lanes look satisfied
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (base + u * 32 < n) {  // warp-uniform
-                unsigned f0 = c[u].x & 0xffffu, f1 = c[u].x >> 16, f2 = c[u].y & 0xffffu;
-                bool sat = (f0 == tu) | (f1 == tu) | (f2 == tu);
-                f0 = f0 == ntu ? 0u : f0;
-                f1 = f1 == ntu ? 0u : f1;
-                f2 = f2 == ntu ? 0u : f2;
-                int zc = (f0 == 0u) + (f1 == 0u) + (f2 == 0u);
-                bool emit = !sat;
-                confl |= emit && zc == 3;
-                unsigned emask = __ballot_sync(kFullMask, emit);
-                trk.update(emask, emit, zc, f0, f1, f2);
-                if (kWrite && emit) dst[out + __popc(emask & lt)] = make_uint2(f0 | (f1 << 16), f2);
-                out += __popc(emask);
-            }
-        }
+    for (int base = 0; base < n; base += 32) {
+        const int idx = base + (int)lane;
+        const bool valid = idx < n;
+        pclause c = valid ? src[idx] : make_uint2(kTomb, kTomb);
+        bool sat;
+        resolve_clause(c.x, c.y, t2, ct, sat);
+        const bool emit = valid && !sat;
+        confl |= emit && ((c.y >> 16) & 3u) == 3u;
+        const unsigned emask = __ballot_sync(kFullMask, emit);
+        if (trk.lit2 == 0) trk.update(emit, c.x, c.y);
+        if (emit) dst[out + __popc(emask & lt)] = c;
+        out += __popc(emask);
     }
     SetInfo s;
     s.n = out;
@@ -126,12 +156,116 @@ __device__ __forceinline__ SetInfo warp_apply(const pclause* src, int n, pclause
     return s;
 }
 
+// ------------------------------------------------------------------------------------------
+// LAZY pass (DFS): the same branch applied IN PLACE to W[0..n_buf), where satisfied clauses
+// become tombstones instead of being squeezed out.  Only clauses that mention the variable are
+// written (a handful per pass), so the pass is a read-only stream:
+//   phase A  chunk by chunk with the ChoiceTracker, until the next unit clause is known;
+//   phase B  the rest of the buffer, kUnroll chunks per step, no warp collectives at all.
+// n_live is the live-clause count on entry.  sticky_conflict: the set already holds a {0,0,0}
+// clause (it can never leave).  Result: s.n = live clauses afterwards.
+template <int kUnroll = 4>
+__device__ __forceinline__ SetInfo warp_apply_lazy(pclause* W, int n_buf, int n_live, int t, bool sticky_conflict,
+                                                   unsigned lane) {
+    const unsigned ct = lit_code(t), t2 = ct | (ct << 16);
+    ChoiceTracker trk;
+    int dropped = 0;
+    bool confl = false;
+    int base = 0;
+    // ---- phase A
+    for (; base < n_buf && trk.lit2 == 0; base += 32) {
+        const int idx = base + (int)lane;
+        const bool valid = idx < n_buf;
+        pclause c = valid ? W[idx] : make_uint2(kTomb, kTomb);
+        bool live = c.x != kTomb;
+        bool sat;
+        if (resolve_clause(c.x, c.y, t2, ct, sat)) {
+            if (sat) { c.x = kTomb; c.y = kTomb; ++dropped; live = false; }
+            else confl |= ((c.y >> 16) & 3u) == 3u;
+            W[idx] = c;
+        }
+        trk.update(live, c.x, c.y);
+    }
+    // ---- phase B
+    for (; base < n_buf; base += 32 * kUnroll) {
+        pclause c[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int idx = base + u * 32 + (int)lane;
+            c[u] = idx < n_buf ? W[idx] : make_uint2(kTomb, kTomb);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (touches(c[u].x, c[u].y, t2, ct)) {
+                bool sat;
+                resolve_clause(c[u].x, c[u].y, t2, ct, sat);
+                if (sat) { c[u].x = kTomb; c[u].y = kTomb; ++dropped; }
+                else confl |= ((c[u].y >> 16) & 3u) == 3u;
+                W[base + u * 32 + (int)lane] = c[u];
+            }
+        }
+    }
+    SetInfo s;
+    s.n = n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
+    s.conflict = (sticky_conflict || __any_sync(kFullMask, confl)) ? 1 : 0;
+    trk.finish(s);
+    return s;
+}
+
+// Read-only classification of one branch (decision nodes look at both children before they
+// commit): live count afterwards and the conflict flag.  kind/lit are not computed.
+template <int kUnroll = 4>
+__device__ __forceinline__ SetInfo warp_classify(const pclause* W, int n_buf, int n_live, int t, bool sticky_conflict,
+                                                 unsigned lane) {
+    const unsigned ct = lit_code(t), t2 = ct | (ct << 16);
+    int dropped = 0;
+    bool confl = false;
+    for (int base = 0; base < n_buf; base += 32 * kUnroll) {
+        pclause c[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int idx = base + u * 32 + (int)lane;
+            c[u] = idx < n_buf ? W[idx] : make_uint2(kTomb, kTomb);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (touches(c[u].x, c[u].y, t2, ct)) {
+                bool sat;
+                resolve_clause(c[u].x, c[u].y, t2, ct, sat);
+                if (sat) ++dropped;
+                else confl |= ((c[u].y >> 16) & 3u) == 3u;
+            }
+        }
+    }
+    SetInfo s;
+    s.n = n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
+    s.conflict = (sticky_conflict || __any_sync(kFullMask, confl)) ? 1 : 0;
+    s.kind = K_EMPTY;
+    s.lit = 0;
+    return s;
+}
+
+// Squeeze the tombstones out of W[0..n_buf) in place (stable).  Returns the live count.
+__device__ __forceinline__ int warp_compact(pclause* W, int n_buf, unsigned lane) {
+    const unsigned lt = lanemask_lt();
+    int out = 0;
+    for (int base = 0; base < n_buf; base += 32) {
+        const int idx = base + (int)lane;
+        pclause c = idx < n_buf ? W[idx] : make_uint2(kTomb, kTomb);
+        const bool live = c.x != kTomb;
+        const unsigned m = __ballot_sync(kFullMask, live);
+        if (live && out + __popc(m & lt) != idx) W[out + __popc(m & lt)] = c;
+        out += __popc(m);
+    }
+    return out;
+}
+
 // 2-bit-per-variable assignment table: 0 unassigned, 1 true, 2 false.
 __device__ __forceinline__ unsigned table_get(const unsigned* table, unsigned var) {
     return (table[var >> 4] >> ((var & 15u) * 2u)) & 3u;
 }
 
-// Re-materialise a clause set from its base under the assignment in `table`
+// Re-materialise a clause set from its base slot under the assignment in `table`
 // (the stable-filter equivalence of SURVEY.md §8a: a node's set == its base filtered by the
 // assignment).  With kTable == false it is a plain copy that also computes the SetInfo.
 template <bool kTable>
@@ -142,29 +276,30 @@ __device__ __forceinline__ SetInfo warp_rebuild(const pclause* __restrict__ base
     int out = 0;
     bool confl = false;
     for (int b = 0; b < nb; b += 32) {
-        int idx = b + (int)lane;
-        bool valid = idx < nb;
-        pclause c = valid ? base[idx] : make_uint2(0u, 0u);
-        unsigned f[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+        const int idx = b + (int)lane;
+        const bool valid = idx < nb;
+        pclause c = valid ? base[idx] : make_uint2(kTomb, kTomb);
         bool sat = false;
-        if (kTable) {
+        if (kTable && valid) {
+            unsigned f[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+            unsigned zc = (c.y >> 16) & 3u;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                int l = sext16(f[j]);
-                if (l != 0) {
-                    unsigned val = table_get(table, (unsigned)(l < 0 ? -l : l));
-                    unsigned truth = l > 0 ? 1u : 2u;  // value of the variable that makes l true
+                if (f[j] != 0u) {
+                    const unsigned val = table_get(table, f[j] >> 1);
+                    const unsigned truth = (f[j] & 1u) ? 2u : 1u;  // variable value that makes the literal true
                     if (val == truth) sat = true;
-                    else if (val != 0u) f[j] = 0u;
+                    else if (val != 0u) { f[j] = 0u; ++zc; }
                 }
             }
+            c.x = f[0] | (f[1] << 16);
+            c.y = f[2] | (zc << 16);
         }
-        int zc = (f[0] == 0u) + (f[1] == 0u) + (f[2] == 0u);
-        bool emit = valid && !sat;
-        confl |= emit && zc == 3;
-        unsigned emask = __ballot_sync(kFullMask, emit);
-        trk.update(emask, emit, zc, f[0], f[1], f[2]);
-        if (emit) W[out + __popc(emask & lt)] = make_uint2(f[0] | (f[1] << 16), f[2]);
+        const bool emit = valid && !sat;
+        confl |= emit && ((c.y >> 16) & 3u) == 3u;
+        const unsigned emask = __ballot_sync(kFullMask, emit);
+        if (trk.lit2 == 0) trk.update(emit, c.x, c.y);
+        if (emit) W[out + __popc(emask & lt)] = c;
         out += __popc(emask);
     }
     SetInfo s;

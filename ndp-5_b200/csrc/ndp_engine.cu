@@ -152,7 +152,7 @@ bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
     for (size_t k = 0; k < n; ++k) {
         for (int j = 0; j < 3; ++j) {
             int l = c3[3 * k + j];
-            if (l > kMaxLit || l < -kMaxLit) return false;
+            if (l > kMaxVar || l < -kMaxVar) return false;
             int v = l < 0 ? -l : l;
             if (v > max_var) max_var = v;
         }
@@ -198,7 +198,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     f->stride = std::max(n_clauses, (size_t)1);
     std::vector<pclause> packed(f->stride);
     if (!pack_host(clauses3, n_clauses, packed.data(), f->max_var))
-        return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32767 (16-bit clause packing)");
+        return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
     if ((rc = ensure_buf(f.get(), 0, 64))) return rc;
     CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
 
@@ -348,9 +348,11 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
         f->get_clauses.resize((size_t)e.n * 3 + 1);
         for (int32_t c = 0; c < e.n; ++c) {
             const pclause p = f->get_packed[c];
-            f->get_clauses[3 * c] = sext16(p.x & 0xffffu);
-            f->get_clauses[3 * c + 1] = sext16(p.x >> 16);
-            f->get_clauses[3 * c + 2] = sext16(p.y & 0xffffu);
+            int l0, l1, l2;
+            unpack_clause(p, l0, l1, l2);
+            f->get_clauses[3 * c] = l0;
+            f->get_clauses[3 * c + 1] = l1;
+            f->get_clauses[3 * c + 2] = l2;
         }
         if (clauses3) *clauses3 = f->get_clauses.data();
         if (n_clauses) *n_clauses = (size_t)e.n;
@@ -390,7 +392,7 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
         for (size_t k = k0; k < k1; ++k) {
             size_t n = clause_offsets[k + 1] - clause_offsets[k];
             if (!pack_host(clauses3 + 3 * clause_offsets[k], n, stage.data() + (k - k0) * stride, f->max_var))
-                return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32767 (16-bit clause packing)");
+                return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
             f->entries.push_back(Entry{0, (uint32_t)k, (int32_t)n, -1});
         }
         CUDA_TRY(cudaMemcpy(f->buf[0] + k0 * stride, stage.data(), (k1 - k0) * stride * sizeof(pclause),

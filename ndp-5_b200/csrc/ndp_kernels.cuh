@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) bfs_expand_kernel(const pclause* __restri
                 const int t = b == 0 ? var : -var;   // b=0: LA (i := true), b=1: RA (i := false)
                 // the branch that falsifies a unit clause always emits {0,0,0}: never open
                 if (nd.kind == K_UNIT && t != nd.lit) continue;
-                SetInfo s = warp_apply<true>(A, nd.n, dst + ((size_t)2 * j + b) * stride, t, lane);
+                SetInfo s = warp_apply_copy(A, nd.n, dst + ((size_t)2 * j + b) * stride, t, lane);
                 if (s.n == 0) ch[b].empty = 1;
                 if (s.n > 0 && !s.conflict) { ch[b].n = s.n; ch[b].kind = s.kind; ch[b].lit = s.lit; }
             }
@@ -115,6 +115,8 @@ __global__ void dfs_kernel(const DfsParams p) {
         for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
         int ntrail = 0;
         SetInfo cur = warp_rebuild<false>(base, nb, W, nullptr, lane);
+        int n_buf = cur.n;                 // records in W (live + tombstones)
+        bool sticky = cur.conflict != 0;   // a {0,0,0} clause can never leave the set
         __syncwarp();
         unsigned long long nodes = 0, evals = 0;
         unsigned rebuilds = 0;
@@ -125,45 +127,46 @@ __global__ void dfs_kernel(const DfsParams p) {
             const int var = cur.kind == K_UNIT ? (cur.lit < 0 ? -cur.lit : cur.lit) : cur.lit;
             if (cur.n == 0 || var == 0) { verdict = 1; break; }  // choice()==0: record choices (NDP:817-823)
             evals += (unsigned long long)cur.n;                 // one ResolutionStepWithConflict (NDP:831)
-            bool dead = false;
+            // Which branch is explored next (t), and is its LA sibling left pending?
+            int t = 0;
+            bool pending = false;
             if (cur.kind == K_UNIT) {
-                // i = |x|; the branch making x false emits {0,0,0} (conflict, never pushed); the other one:
-                const int t = cur.lit;
-                SetInfo r = warp_apply<true>(W, cur.n, W, t, lane);
-                __syncwarp();
-                if (lane == 0) trail[ntrail] = (short)t;
-                ++ntrail;
-                if (r.n == 0) { verdict = 1; break; }           // empty branch => model (NDP:843-852 / 863-872)
-                if (r.conflict) dead = true;
-                else cur = r;
+                // i = |x|: the branch that makes x false emits {0,0,0} (conflict, never pushed, NDP:837/857)
+                t = cur.lit;
             } else {
-                SetInfo la = warp_apply<false>(W, cur.n, nullptr, var, lane);
+                SetInfo la = warp_classify(W, n_buf, cur.n, var, sticky, lane);
                 if (la.n == 0) {                                 // LA empty wins before RA is looked at (NDP:843-850)
                     if (lane == 0) trail[ntrail] = (short)var;
                     ++ntrail; verdict = 1; break;
                 }
-                SetInfo ra = warp_apply<false>(W, cur.n, nullptr, -var, lane);
+                SetInfo ra = warp_classify(W, n_buf, cur.n, -var, sticky, lane);
                 if (ra.n == 0) {                                 // NDP:863-870
                     if (lane == 0) trail[ntrail] = (short)(-var);
                     ++ntrail; verdict = 1; break;
                 }
-                const bool la_open = !la.conflict, ra_open = !ra.conflict;
-                if (ra_open) {                                   // RA is on top of the stack: explored first
-                    if (la_open && lane == 0) pend[ntrail >> 5] |= 1u << (ntrail & 31);
-                    if (lane == 0) trail[ntrail] = (short)(-var);
-                    ++ntrail;
-                    cur = warp_apply<true>(W, cur.n, W, -var, lane);
-                    __syncwarp();
-                } else if (la_open) {
-                    if (lane == 0) trail[ntrail] = (short)var;
-                    ++ntrail;
-                    cur = warp_apply<true>(W, cur.n, W, var, lane);
-                    __syncwarp();
-                } else {
-                    dead = true;
+                if (!ra.conflict) { t = -var; pending = !la.conflict; }  // RA is on top of the stack: explored first
+                else if (!la.conflict) t = var;
+            }
+            bool dead = t == 0;
+            if (!dead) {
+                if (lane == 0) {
+                    if (pending) pend[ntrail >> 5] |= 1u << (ntrail & 31);
+                    trail[ntrail] = (short)t;
+                }
+                ++ntrail;
+                SetInfo r = warp_apply_lazy(W, n_buf, cur.n, t, sticky, lane);
+                __syncwarp();
+                if (r.n == 0) { verdict = 1; break; }           // empty branch => model (NDP:843-852 / 863-872)
+                if (r.conflict) dead = true;
+                else {
+                    cur = r;
+                    if (n_buf - cur.n > (n_buf >> 3) + 32) {     // squeeze out tombstones now and then
+                        n_buf = warp_compact(W, n_buf, lane);
+                        __syncwarp();
+                    }
+                    continue;
                 }
             }
-            if (!dead) continue;
             // Backtrack: pop to the deepest decision whose LA sibling is still pending.
             __syncwarp();
             int pos = -1;
@@ -191,6 +194,7 @@ __global__ void dfs_kernel(const DfsParams p) {
             }
             __syncwarp();
             cur = warp_rebuild<true>(base, nb, W, table, lane);
+            n_buf = cur.n;
             __syncwarp();
             ++rebuilds;
         }

@@ -74,7 +74,7 @@ def test_bfs_edge_cases(nd, oracle):
     one = np.array([[1, 2, 3]], dtype=np.int32)
     all_zero_first = np.array([[0, 0, 0], [1, 2, 3]], dtype=np.int32)
     all_zero_mid = np.array([[0, 0, 4], [0, 0, 0], [1, 2, 3]], dtype=np.int32)
-    sparse_ids = np.array([[30000, -32767, 5], [0, 0, -30000], [0, 32767, 7]], dtype=np.int32)
+    sparse_ids = np.array([[30000, -32766, 5], [0, 0, -30000], [0, 32766, 7]], dtype=np.int32)
     for name, A in [("unit_only", unit_only), ("contradictory", contradictory), ("one", one),
                     ("all_zero_first", all_zero_first), ("all_zero_mid", all_zero_mid), ("sparse_ids", sparse_ids)]:
         for D, ovr, Q in [(-1, False, -1), (1, False, -1), (5, False, -1), (100, False, -1), (0, True, 1),
@@ -84,9 +84,13 @@ def test_bfs_edge_cases(nd, oracle):
 
 
 def test_unsupported_literal_width_fails_loudly(nd):
-    with pytest.raises(nd.NdpError) as ei:
-        nd.bfs(np.array([[1, 2, 40000]], dtype=np.int32), 1, False, -1)
-    assert ei.value.code == nd.NDP_E_UNSUPPORTED
+    for bad in (40000, 32767, -32767):
+        with pytest.raises(nd.NdpError) as ei:
+            nd.bfs(np.array([[1, 2, bad]], dtype=np.int32), 1, False, -1)
+        assert ei.value.code == nd.NDP_E_UNSUPPORTED
+        with pytest.raises(nd.NdpError) as ei:
+            nd.frontier_from_host([(np.array([[1, 2, bad]], dtype=np.int32), np.zeros(0, np.int32))])
+        assert ei.value.code == nd.NDP_E_UNSUPPORTED
 
 
 # ------------------------------------------------------------------------------------------ DFS
