@@ -43,7 +43,8 @@ typedef struct ndp_stats {
     uint64_t clause_evals;   /* sum of |A| over nodes that ran the resolution pass (NDP:664) */
     uint64_t rebuilds;       /* sibling re-materialisations (engine detail, not in the reference) */
     double kernel_ms;        /* device time of the DFS kernel(s), CUDA events */
-    double h2d_ms, d2h_ms;   /* transfers done inside the call */
+    uint64_t h2d_bytes;      /* host->device bytes moved inside the call */
+    uint64_t d2h_bytes;      /* device->host bytes moved inside the call */
     uint64_t launches;       /* kernels launched by the call */
 } ndp_stats;
 
@@ -70,6 +71,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
 /* BFS clause evaluations (sum of |A| over expanded nodes) and device time of the last ndp_bfs
  * that produced this frontier; 0 for frontiers built by ndp_frontier_from_host. */
 int ndp_frontier_bfs_stats(const ndp_frontier* f, uint64_t* clause_evals, double* kernel_ms, uint64_t* launches);
+/* host<->device bytes the BFS (or ndp_frontier_from_host) moved while building this frontier */
+int ndp_frontier_bfs_bytes(const ndp_frontier* f, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 size_t ndp_frontier_size(const ndp_frontier* f);
 

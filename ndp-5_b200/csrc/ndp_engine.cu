@@ -72,7 +72,7 @@ struct ndp_frontier {
     std::vector<int32_t> flat_choices;
     std::vector<size_t> flat_off;
     // BFS stats
-    uint64_t bfs_evals = 0, bfs_launches = 0;
+    uint64_t bfs_evals = 0, bfs_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     double bfs_kernel_ms = 0;
     // scratch for ndp_frontier_get
     std::vector<int32_t> get_clauses, get_choices;
@@ -201,6 +201,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
     if ((rc = ensure_buf(f.get(), 0, 64))) return rc;
     CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
+    f->h2d_bytes += n_clauses * sizeof(pclause);
 
     struct HostNode { uint32_t slot; int32_t n, kind, lit, tree; };
     std::vector<HostNode> cur, next;
@@ -271,6 +272,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         cudaEventElapsedTime(&ms, ev0, ev1);
         f->bfs_kernel_ms += ms;
         f->bfs_launches += 1;
+        f->h2d_bytes += need * sizeof(BfsNode);
+        f->d2h_bytes += 2 * need * sizeof(BfsChild);
 
         next.clear();
         size_t s = m;
@@ -324,6 +327,13 @@ int ndp_frontier_bfs_stats(const ndp_frontier* f, uint64_t* clause_evals, double
     if (clause_evals) *clause_evals = f->bfs_evals;
     if (kernel_ms) *kernel_ms = f->bfs_kernel_ms;
     if (launches) *launches = f->bfs_launches;
+    return NDP_OK;
+}
+
+int ndp_frontier_bfs_bytes(const ndp_frontier* f, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (h2d_bytes) *h2d_bytes = f->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = f->d2h_bytes;
     return NDP_OK;
 }
 
@@ -397,6 +407,7 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
         }
         CUDA_TRY(cudaMemcpy(f->buf[0] + k0 * stride, stage.data(), (k1 - k0) * stride * sizeof(pclause),
                             cudaMemcpyHostToDevice));
+        f->h2d_bytes += (k1 - k0) * stride * sizeof(pclause);
     }
     f->flat_off.assign(choice_offsets, choice_offsets + count + 1);
     size_t base = count ? choice_offsets[0] : 0;
@@ -613,6 +624,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
             }
     }
     if (stats) {
+        stats->h2d_bytes += 8 + 4;                                   // early-exit word + work counter
+        stats->d2h_bytes += nl * (1 + 8 + 8 + 4) + (win != SIZE_MAX && model ? (size_t)n_warps * 12 + model->size() * 4 : 0);
         stats->nodes += tn;
         stats->clause_evals += te;
         stats->rebuilds += tr;
@@ -717,6 +730,7 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         for (int i = 0; i < n_gpus; ++i) {
             stats->nodes += st[i].nodes; stats->clause_evals += st[i].clause_evals; stats->rebuilds += st[i].rebuilds;
             stats->kernel_ms = std::max(stats->kernel_ms, st[i].kernel_ms); stats->launches += st[i].launches;
+            stats->h2d_bytes += st[i].h2d_bytes; stats->d2h_bytes += st[i].d2h_bytes;
         }
     if (winner) *winner = win;
     if (who >= 0) {

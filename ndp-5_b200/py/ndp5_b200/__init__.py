@@ -32,7 +32,7 @@ class NdpError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [("nodes", C.c_uint64), ("clause_evals", C.c_uint64), ("rebuilds", C.c_uint64),
-                ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("kernel_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint64)]
 
     def as_dict(self):
@@ -52,6 +52,7 @@ def _load():
         "ndp_bfs": (C.c_int, [_i32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                               C.POINTER(C.c_int), C.POINTER(C.c_int), _szp]),
         "ndp_frontier_bfs_stats": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_double), _u64p]),
+        "ndp_frontier_bfs_bytes": (C.c_int, [C.c_void_p, _u64p, _u64p]),
         "ndp_frontier_size": (C.c_size_t, [C.c_void_p]),
         "ndp_frontier_get": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(_i32p), _szp, C.POINTER(_i32p), _szp]),
         "ndp_frontier_dims": (C.c_int, [C.c_void_p, C.c_size_t, _szp, _szp]),
@@ -117,7 +118,10 @@ class Frontier:
     def bfs_stats(self):
         ev, ms, ln = C.c_uint64(0), C.c_double(0), C.c_uint64(0)
         _check(lib.ndp_frontier_bfs_stats(self.h, C.byref(ev), C.byref(ms), C.byref(ln)))
-        return dict(clause_evals=ev.value, kernel_ms=ms.value, launches=ln.value)
+        h2d, d2h = C.c_uint64(0), C.c_uint64(0)
+        _check(lib.ndp_frontier_bfs_bytes(self.h, C.byref(h2d), C.byref(d2h)))
+        return dict(clause_evals=ev.value, kernel_ms=ms.value, launches=ln.value, h2d_bytes=h2d.value,
+                    d2h_bytes=d2h.value)
 
     def dfs_shard(self, first=0, stride=1, early_exit=False, exit_flag=None, model_cap=1 << 16, counters=True):
         n = len(self)

@@ -126,6 +126,17 @@ void ref_frontier_copy(void* h, size_t k, int32_t* clauses3, int32_t* choices) {
     if (choices) for (size_t j = 0; j < e.second.size(); ++j) choices[j] = e.second[j];
 }
 void ref_frontier_free(void* h) { delete static_cast<Frontier*>(h); }
+// Build a queue from host arrays (offsets have count+1 entries, in clauses / in ints), so the
+// reference's DFS can be timed on a frontier that was produced elsewhere.
+void* ref_frontier_from_arrays(const int32_t* c3, const size_t* cl_off, const int32_t* ch, const size_t* ch_off,
+                               size_t count) {
+    Frontier* f = new Frontier;
+    f->reserve(count);
+    for (size_t k = 0; k < count; ++k)
+        f->emplace_back(to_set(c3 + 3 * cl_off[k], cl_off[k + 1] - cl_off[k]),
+                        std::vector<int>(ch + ch_off[k], ch + ch_off[k + 1]));
+    return f;
+}
 
 // ---- DFS -----------------------------------------------------------------------------------
 // returns number of models (0 => UNSAT); the first model is copied to `model` (<= cap ints).

@@ -187,6 +187,20 @@ class RefLib(_Common):
         return dict(seconds=sec, verdict=verdict[:count].copy(), winner=winner.value, model=model[:ml.value].copy(),
                     nodes=nodes[:count].copy())
 
+    def frontier_from_arrays(self, items):
+        f = self._fn("frontier_from_arrays", C.c_void_p, [_i32p, _szp, _i32p, _szp, C.c_size_t])
+        cl_off, ch_off = [0], [0]
+        for cl, ch in items:
+            cl_off.append(cl_off[-1] + len(cl))
+            ch_off.append(ch_off[-1] + len(ch))
+        cl_all = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32).reshape(-1, 3) for c, _ in items])
+                                      if items else np.zeros((0, 3), np.int32))
+        ch_all = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32).reshape(-1) for _, c in items])
+                                      if items else np.zeros(0, np.int32))
+        clo, cho = np.asarray(cl_off, dtype=np.uintp), np.asarray(ch_off, dtype=np.uintp)
+        return f(cl_all.ctypes.data_as(_i32p), clo.ctypes.data_as(_szp), ch_all.ctypes.data_as(_i32p),
+                 cho.ctypes.data_as(_szp), len(items))
+
     def save_bfs(self, handle, script, filename, pid, flag, outdir, bfs_time):
         buf = C.create_string_buffer(4096)
         self._save(handle, script.encode(), filename.encode(), pid.encode(), flag.encode(), outdir.encode(),
