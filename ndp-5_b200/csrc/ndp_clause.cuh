@@ -136,18 +136,29 @@ __device__ __forceinline__ SetInfo warp_apply_copy(const pclause* __restrict__ s
     ChoiceTracker trk;
     int out = 0;
     bool confl = false;
-    for (int base = 0; base < n; base += 32) {
-        const int idx = base + (int)lane;
-        const bool valid = idx < n;
-        pclause c = valid ? src[idx] : make_uint2(kTomb, kTomb);
-        bool sat;
-        resolve_clause(c.x, c.y, t2, ct, sat);
-        const bool emit = valid && !sat;
-        confl |= emit && ((c.y >> 16) & 3u) == 3u;
-        const unsigned emask = __ballot_sync(kFullMask, emit);
-        if (trk.lit2 == 0) trk.update(emit, c.x, c.y);
-        if (emit) dst[out + __popc(emask & lt)] = c;
-        out += __popc(emask);
+    constexpr int kU = 8;   // global loads in flight per lane: the pass is latency-bound on narrow levels
+    for (int base = 0; base < n; base += 32 * kU) {
+        pclause cc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int idx = base + u * 32 + (int)lane;
+            cc[u] = idx < n ? __ldg(&src[idx]) : make_uint2(kTomb, kTomb);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (base + u * 32 < n) {   // warp-uniform
+                pclause c = cc[u];
+                const bool valid = c.x != kTomb;   // src holds no tombstones; padding lanes do
+                bool sat;
+                resolve_clause(c.x, c.y, t2, ct, sat);
+                const bool emit = valid && !sat;
+                confl |= emit && ((c.y >> 16) & 3u) == 3u;
+                const unsigned emask = __ballot_sync(kFullMask, emit);
+                if (trk.lit2 == 0) trk.update(emit, c.x, c.y);
+                if (emit) dst[out + __popc(emask & lt)] = c;
+                out += __popc(emask);
+            }
+        }
     }
     SetInfo s;
     s.n = out;
@@ -157,96 +168,117 @@ __device__ __forceinline__ SetInfo warp_apply_copy(const pclause* __restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------
-// LAZY pass (DFS): the same branch applied IN PLACE to W[0..n_buf), where satisfied clauses
-// become tombstones instead of being squeezed out.  Only clauses that mention the variable are
-// written (a handful per pass), so the pass is a read-only stream:
-//   phase A  chunk by chunk with the ChoiceTracker, until the next unit clause is known;
-//   phase B  the rest of the buffer, kUnroll chunks per step, no warp collectives at all.
-// n_live is the live-clause count on entry.  sticky_conflict: the set already holds a {0,0,0}
-// clause (it can never leave).  Result: s.n = live clauses afterwards.
-template <int kUnroll = 4>
-__device__ __forceinline__ SetInfo warp_apply_lazy(pclause* W, int n_buf, int n_live, int t, bool sticky_conflict,
-                                                   unsigned lane) {
+// LAZY passes (DFS).  The working set W[0..n_buf) is updated IN PLACE: satisfied clauses become
+// tombstones instead of being squeezed out, and only clauses that mention the variable are
+// written (a handful per pass), so a pass is a read-only stream over shared memory.
+// Invariant kept by warp_rebuild / warp_compact: W is padded with tombstones up to the next
+// multiple of kGroup records, so the streaming loops need no bounds checks.
+constexpr int kStreamUnroll = 4;
+constexpr int kGroup = 32 * kStreamUnroll;
+__host__ __device__ __forceinline__ int pad_up(int n) { return (n + kGroup - 1) / kGroup * kGroup; }
+
+__device__ __forceinline__ void pad_tail(pclause* W, int n, unsigned lane) {
+    for (int idx = n + (int)lane; idx < pad_up(n); idx += 32) W[idx] = make_uint2(kTomb, kTomb);
+}
+
+// A touched clause, parked in registers until the lane meets its next one (or the pass ends):
+// the stream itself stays free of the (divergent) resolution code.
+struct Parked {
+    int idx = -1;
+    unsigned x = 0, y = 0;
+};
+template <bool kWrite>
+__device__ __forceinline__ void settle(pclause* W, Parked& p, unsigned t2, unsigned ct, int& dropped, bool& confl) {
+    bool sat;
+    resolve_clause(p.x, p.y, t2, ct, sat);
+    if (sat) { p.x = kTomb; p.y = kTomb; ++dropped; }
+    else confl |= ((p.y >> 16) & 3u) == 3u;
+    if (kWrite) W[p.idx] = make_uint2(p.x, p.y);
+    p.idx = -1;
+}
+
+// One branch of the resolution step ("literal t becomes true") over the whole set.
+//   kWrite = true : apply it (ResolutionStepWithConflict for the branch that is explored,
+//                   NDP-5_6_7.cpp:654-697) and report what choice() will return next:
+//       phase A  chunk by chunk with the ChoiceTracker, until the next unit clause is known;
+//       phase B  the rest of the buffer, kStreamUnroll chunks per step, no warp collectives.
+//   kWrite = false: classify only (decision nodes look at both children before committing).
+// n_live = live clauses on entry; sticky_conflict = the set already holds a {0,0,0} clause
+// (it can never leave).  Result: s.n = live clauses afterwards, s.conflict, s.kind/lit (kWrite).
+template <bool kWrite>
+__device__ __forceinline__ SetInfo warp_pass_lazy(pclause* W, int n_buf, int n_live, int t, bool sticky_conflict,
+                                                  unsigned lane) {
     const unsigned ct = lit_code(t), t2 = ct | (ct << 16);
+    const int n_pad = pad_up(n_buf);
     ChoiceTracker trk;
     int dropped = 0;
     bool confl = false;
     int base = 0;
-    // ---- phase A
-    for (; base < n_buf && trk.lit2 == 0; base += 32) {
-        const int idx = base + (int)lane;
-        const bool valid = idx < n_buf;
-        pclause c = valid ? W[idx] : make_uint2(kTomb, kTomb);
-        bool live = c.x != kTomb;
-        bool sat;
-        if (resolve_clause(c.x, c.y, t2, ct, sat)) {
-            if (sat) { c.x = kTomb; c.y = kTomb; ++dropped; live = false; }
-            else confl |= ((c.y >> 16) & 3u) == 3u;
-            W[idx] = c;
-        }
-        trk.update(live, c.x, c.y);
-    }
-    // ---- phase B
-    for (; base < n_buf; base += 32 * kUnroll) {
-        pclause c[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int idx = base + u * 32 + (int)lane;
-            c[u] = idx < n_buf ? W[idx] : make_uint2(kTomb, kTomb);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (touches(c[u].x, c[u].y, t2, ct)) {
+    if (kWrite) {
+        // ---- phase A: in order, with the tracker, until the first live two-zero clause shows up
+        for (; base < n_pad && trk.lit2 == 0; base += 32) {
+            const int idx = base + (int)lane;
+            pclause c = W[idx];
+            bool live = c.x != kTomb;
+            const unsigned zc = (c.y >> 16) & 3u;
+            const bool touched = touches(c.x, c.y, t2, ct);
+            // can this chunk change the tracker or the set at all?
+            const bool interesting = live && (touched || zc == 2u || (trk.lit1 == 0 && zc == 1u) || !trk.have_first);
+            if (__ballot_sync(kFullMask, interesting) == 0u) continue;
+            if (touched) {
                 bool sat;
-                resolve_clause(c[u].x, c[u].y, t2, ct, sat);
-                if (sat) { c[u].x = kTomb; c[u].y = kTomb; ++dropped; }
-                else confl |= ((c[u].y >> 16) & 3u) == 3u;
-                W[base + u * 32 + (int)lane] = c[u];
+                resolve_clause(c.x, c.y, t2, ct, sat);
+                if (sat) { c.x = kTomb; c.y = kTomb; ++dropped; live = false; }
+                else confl |= ((c.y >> 16) & 3u) == 3u;
+                W[idx] = c;
+            }
+            trk.update(live, c.x, c.y);
+        }
+        // finish the current group chunk by chunk so that phase B starts group-aligned
+        for (; base < n_pad && (base % kGroup) != 0; base += 32) {
+            const int idx = base + (int)lane;
+            pclause c = W[idx];
+            if (touches(c.x, c.y, t2, ct)) {
+                Parked p;
+                p.idx = idx; p.x = c.x; p.y = c.y;
+                settle<true>(W, p, t2, ct, dropped, confl);
             }
         }
     }
-    SetInfo s;
-    s.n = n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
-    s.conflict = (sticky_conflict || __any_sync(kFullMask, confl)) ? 1 : 0;
-    trk.finish(s);
-    return s;
-}
-
-// Read-only classification of one branch (decision nodes look at both children before they
-// commit): live count afterwards and the conflict flag.  kind/lit are not computed.
-template <int kUnroll = 4>
-__device__ __forceinline__ SetInfo warp_classify(const pclause* W, int n_buf, int n_live, int t, bool sticky_conflict,
-                                                 unsigned lane) {
-    const unsigned ct = lit_code(t), t2 = ct | (ct << 16);
-    int dropped = 0;
-    bool confl = false;
-    for (int base = 0; base < n_buf; base += 32 * kUnroll) {
-        pclause c[kUnroll];
+    // ---- phase B: pure stream
+    Parked park;
+    for (; base < n_pad; base += kGroup) {
+        pclause c[kStreamUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int idx = base + u * 32 + (int)lane;
-            c[u] = idx < n_buf ? W[idx] : make_uint2(kTomb, kTomb);
+        for (int u = 0; u < kStreamUnroll; ++u) c[u] = W[base + u * 32 + (int)lane];
+        static_assert(kStreamUnroll == 4, "the select chain below is written for 4 chunks per group");
+        const bool h0 = touches(c[0].x, c[0].y, t2, ct), h1 = touches(c[1].x, c[1].y, t2, ct);
+        const bool h2 = touches(c[2].x, c[2].y, t2, ct), h3 = touches(c[3].x, c[3].y, t2, ct);
+        if (!(h0 | h1 | h2 | h3)) continue;
+        unsigned hit = (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
+        while (hit) {   // rare and divergent: a lane that meets a clause of the variable parks it
+            const int u = __ffs(hit) - 1;
+            hit &= hit - 1u;
+            if (park.idx >= 0) settle<kWrite>(W, park, t2, ct, dropped, confl);
+            park.idx = base + u * 32 + (int)lane;
+            park.x = u == 0 ? c[0].x : u == 1 ? c[1].x : u == 2 ? c[2].x : c[3].x;
+            park.y = u == 0 ? c[0].y : u == 1 ? c[1].y : u == 2 ? c[2].y : c[3].y;
         }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (touches(c[u].x, c[u].y, t2, ct)) {
-                bool sat;
-                resolve_clause(c[u].x, c[u].y, t2, ct, sat);
-                if (sat) ++dropped;
-                else confl |= ((c[u].y >> 16) & 3u) == 3u;
-            }
-        }
+    }
+    if (__any_sync(kFullMask, park.idx >= 0)) {       // one convergent round for the parked clauses
+        if (park.idx >= 0) settle<kWrite>(W, park, t2, ct, dropped, confl);
     }
     SetInfo s;
     s.n = n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
     s.conflict = (sticky_conflict || __any_sync(kFullMask, confl)) ? 1 : 0;
     s.kind = K_EMPTY;
     s.lit = 0;
+    if (kWrite) trk.finish(s);
     return s;
 }
 
-// Squeeze the tombstones out of W[0..n_buf) in place (stable).  Returns the live count.
-__device__ __forceinline__ int warp_compact(pclause* W, int n_buf, unsigned lane) {
+// Squeeze the tombstones out of W[0..n_buf) in place (stable) and re-pad.  Returns the live count.
+__device__ __noinline__ int warp_compact(pclause* W, int n_buf, unsigned lane) {
     const unsigned lt = lanemask_lt();
     int out = 0;
     for (int base = 0; base < n_buf; base += 32) {
@@ -257,6 +289,8 @@ __device__ __forceinline__ int warp_compact(pclause* W, int n_buf, unsigned lane
         if (live && out + __popc(m & lt) != idx) W[out + __popc(m & lt)] = c;
         out += __popc(m);
     }
+    __syncwarp();
+    pad_tail(W, out, lane);
     return out;
 }
 
@@ -269,7 +303,7 @@ __device__ __forceinline__ unsigned table_get(const unsigned* table, unsigned va
 // (the stable-filter equivalence of SURVEY.md §8a: a node's set == its base filtered by the
 // assignment).  With kTable == false it is a plain copy that also computes the SetInfo.
 template <bool kTable>
-__device__ __forceinline__ SetInfo warp_rebuild(const pclause* __restrict__ base, int nb, pclause* W,
+__device__ __noinline__ SetInfo warp_rebuild(const pclause* __restrict__ base, int nb, pclause* W,
                                                 const unsigned* table, unsigned lane) {
     const unsigned lt = lanemask_lt();
     ChoiceTracker trk;
@@ -302,6 +336,8 @@ __device__ __forceinline__ SetInfo warp_rebuild(const pclause* __restrict__ base
         if (emit) W[out + __popc(emask & lt)] = c;
         out += __popc(emask);
     }
+    __syncwarp();
+    pad_tail(W, out, lane);   // the streaming passes rely on a tombstone-padded tail
     SetInfo s;
     s.n = out;
     s.conflict = __any_sync(kFullMask, confl) ? 1 : 0;

@@ -147,6 +147,65 @@ int ensure_buf(ndp_frontier* f, int b, size_t slots) {
     return NDP_OK;
 }
 
+// Device-resident bookkeeping of the BFS level loop (freed on scope exit).
+struct BfsLevelState {
+    BfsNode* nodes[2] = {nullptr, nullptr};
+    int32_t* node_tree[2] = {nullptr, nullptr};
+    BfsChild* children = nullptr;
+    int32_t *tree_parent = nullptr, *tree_lit = nullptr;
+    BfsLevelTotals* totals = nullptr;
+    size_t node_cap = 0, tree_cap = 0, tree_count = 0;
+    int cur = 0;
+
+    template <class T> static int grow(T*& p, size_t old_n, size_t new_n) {
+        T* q = nullptr;
+        CUDA_TRY(cudaMalloc(&q, new_n * sizeof(T)));
+        if (p && old_n) CUDA_TRY(cudaMemcpy(q, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice));
+        if (p) cudaFree(p);
+        p = q;
+        return NDP_OK;
+    }
+    int reserve_nodes(size_t want) {
+        if (!totals) CUDA_TRY(cudaMalloc(&totals, sizeof(BfsLevelTotals)));
+        if (want <= node_cap) return NDP_OK;
+        size_t cap = std::max(want, std::max(node_cap * 2, (size_t)4096));
+        int rc;
+        for (int b = 0; b < 2; ++b) {
+            if ((rc = grow(nodes[b], node_cap, cap))) return rc;
+            if ((rc = grow(node_tree[b], node_cap, cap))) return rc;
+        }
+        if (children) cudaFree(children);
+        children = nullptr;
+        CUDA_TRY(cudaMalloc(&children, cap * sizeof(BfsChild)));
+        node_cap = cap;
+        return NDP_OK;
+    }
+    int reserve_tree(size_t want) {
+        if (want <= tree_cap) return NDP_OK;
+        size_t cap = std::max(want, std::max(tree_cap * 2, (size_t)65536));
+        int rc;
+        if ((rc = grow(tree_parent, tree_count, cap))) return rc;
+        if ((rc = grow(tree_lit, tree_count, cap))) return rc;
+        tree_cap = cap;
+        return NDP_OK;
+    }
+    int download_level(size_t m, std::vector<BfsNode>& h_nodes, std::vector<int32_t>& h_tree, uint64_t& d2h) {
+        h_nodes.resize(m);
+        h_tree.resize(m);
+        CUDA_TRY(cudaMemcpy(h_nodes.data(), nodes[cur], m * sizeof(BfsNode), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_tree.data(), node_tree[cur], m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        d2h += m * (sizeof(BfsNode) + sizeof(int32_t));
+        return NDP_OK;
+    }
+    ~BfsLevelState() {
+        for (int b = 0; b < 2; ++b) { if (nodes[b]) cudaFree(nodes[b]); if (node_tree[b]) cudaFree(node_tree[b]); }
+        if (children) cudaFree(children);
+        if (tree_parent) cudaFree(tree_parent);
+        if (tree_lit) cudaFree(tree_lit);
+        if (totals) cudaFree(totals);
+    }
+};
+
 // pack an int32 n x 3 clause array; returns false if a literal does not fit 16 bits
 bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
     for (size_t k = 0; k < n; ++k) {
@@ -203,84 +262,120 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
     f->h2d_bytes += n_clauses * sizeof(pclause);
 
-    struct HostNode { uint32_t slot; int32_t n, kind, lit, tree; };
-    std::vector<HostNode> cur, next;
-    {
-        HostNode r{0, (int32_t)n_clauses, 0, 0, 0};
-        host_setinfo(clauses3, n_clauses, r.kind, r.lit);
-        cur.push_back(r);
-    }
-    f->tree_parent.push_back(-1);
-    f->tree_lit.push_back(0);
-
     const int D = max_iterations, Q = max_queues;
     const bool ovr = override_max_iterations != 0;
     long long it = 0, task_count = 1;
     int cur_buf = 0;
-    BfsNode* d_nodes = nullptr;
-    BfsChild* d_children = nullptr;
-    size_t d_cap = 0;
-    std::vector<BfsNode> h_nodes;
-    std::vector<BfsChild> h_children;
-    cudaEvent_t ev0, ev1;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
+    size_t m = 1;
+
+    // Level state lives on the device: node list (slot, n, kind, lit), each node's index in the
+    // choice tree, the tree itself (parent, literal).  The host reads back one 32-byte totals
+    // record per level, and the full per-child metadata only for levels in which a stop test
+    // can fire.
+    BfsLevelState st;
     int status = NDP_OK;
-    size_t E = 0;           // nodes of `cur` consumed when the loop stops
-    bool have_next = false; // `next` holds children that belong to the frontier
+    {
+        BfsNode root{0, (int32_t)n_clauses, 0, 0};
+        host_setinfo(clauses3, n_clauses, root.kind, root.lit);
+        if ((status = st.reserve_nodes(1)) || (status = st.reserve_tree(1))) return status;
+        int32_t zero = 0, minus1 = -1;
+        CUDA_TRY(cudaMemcpy(st.nodes[0], &root, sizeof root, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(st.node_tree[0], &zero, 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(st.tree_parent, &minus1, 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(st.tree_lit, &zero, 4, cudaMemcpyHostToDevice));
+        st.tree_count = 1;
+        f->h2d_bytes += sizeof root + 12;
+    }
+    std::vector<cudaEvent_t> evs;          // one (start, stop) pair per level, summed at the end
+
+    std::vector<BfsNode> h_nodes;          // current level, only materialised on the host when needed
+    std::vector<int32_t> h_node_tree;
+    std::vector<BfsChild> h_children;
+    std::vector<Entry> final_entries;
+    struct Pushed { int32_t parent_tree, lit; };
+    std::vector<Pushed> host_tree_tail;    // tree entries created by the host walk of the stop level
+    bool done = false;
 
     // Level-synchronous restatement of the FIFO loop NDP:893-937: a FIFO
     // queue only ever holds the unexpanded rest of level L followed by the level-L+1 children
     // pushed so far, so walking one level in order with the running queue size `s` reproduces
     // every stop test at the exact pop it would fire.
-    for (;;) {
-        const size_t m = cur.size();
-        E = 0;
-        have_next = false;
+    while (!done) {
         if (m == 0) break;                                           // queue empty (NDP:893)
-        if (Q > 0 && m >= (size_t)Q) break;                          // NDP:894-895 before the level's first pop
-        if (D == -1 && !ovr) break;                                  // NDP:896-897 (iterations >= -1 always)
+        bool stop_at_top = (Q > 0 && m >= (size_t)Q) || (D == -1 && !ovr);   // NDP:894-897 before the first pop
         size_t need = m;
-        if (Q <= 0) {                                                // -d budget known in advance
+        if (!stop_at_top && Q <= 0) {                                // -d budget known in advance
             long long R = (long long)D - it;
             need = (size_t)std::min<long long>((long long)m, std::max<long long>(R, 1));
         }
-        if ((status = ensure_buf(f.get(), cur_buf ^ 1, 2 * need))) break;
-        if (d_cap < need) {
-            if (d_nodes) cudaFree(d_nodes);
-            if (d_children) cudaFree(d_children);
-            d_cap = std::max(need * 2, (size_t)1024);
-            if (cudaMalloc(&d_nodes, d_cap * sizeof(BfsNode)) != cudaSuccess ||
-                cudaMalloc(&d_children, 2 * d_cap * sizeof(BfsChild)) != cudaSuccess) {
-                status = fail(NDP_E_NOMEM, "BFS level metadata allocation failed");
-                break;
-            }
+        // can any stop test fire inside this level?  -q: the queue never exceeds m + pushes <= 2m;
+        // -d: the level is consumed whole iff it + m < D.
+        const bool safe = !stop_at_top && (Q > 0 ? 2 * m < (size_t)Q : (it + (long long)m < (long long)D));
+        if (stop_at_top) {
+            if ((status = st.download_level(m, h_nodes, h_node_tree, f->d2h_bytes))) break;
+            for (size_t j = 0; j < m; ++j) final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j]});
+            break;
         }
-        h_nodes.resize(need);
-        for (size_t j = 0; j < need; ++j) h_nodes[j] = BfsNode{cur[j].slot, cur[j].n, cur[j].kind, cur[j].lit};
-        cudaMemcpyAsync(d_nodes, h_nodes.data(), need * sizeof(BfsNode), cudaMemcpyHostToDevice, 0);
+        {
+            // grow the (dead) target buffer geometrically, but never past what the stop rule
+            // allows a level to reach: width <= Q under -q, <= D+1 under -d
+            size_t want = 2 * need;
+            if (f->cap_slots[cur_buf ^ 1] < want) {
+                size_t bound = SIZE_MAX;
+                if (Q > 0) bound = 2 * (size_t)Q;
+                else if (D > 0) bound = 2 * ((size_t)D + 1);
+                want = std::min(std::max(want, f->cap_slots[cur_buf ^ 1] * 2), std::max(bound, want));
+            }
+            status = ensure_buf(f.get(), cur_buf ^ 1, want);
+            if (status == NDP_E_NOMEM && want > 2 * need) {   // head-room did not fit: take the exact size
+                cudaGetLastError();
+                status = ensure_buf(f.get(), cur_buf ^ 1, 2 * need);
+            }
+            if (status) break;
+        }
+        if ((status = st.reserve_nodes(2 * need)) || (status = st.reserve_tree(st.tree_count + 2 * need))) break;
         const int warps_per_block = 8;
         int grid = (int)std::min<size_t>((need + warps_per_block - 1) / warps_per_block, (size_t)148 * 16);
-        cudaEventRecord(ev0, 0);
-        bfs_expand_kernel<<<grid, warps_per_block * 32>>>(f->buf[cur_buf], f->buf[cur_buf ^ 1], f->stride, d_nodes,
-                                                          (int)need, d_children);
-        cudaEventRecord(ev1, 0);
-        h_children.resize(2 * need);
-        cudaError_t ce = cudaMemcpy(h_children.data(), d_children, 2 * need * sizeof(BfsChild), cudaMemcpyDeviceToHost);
+        cudaEvent_t ea, eb;
+        cudaEventCreate(&ea);
+        cudaEventCreate(&eb);
+        evs.push_back(ea);
+        evs.push_back(eb);
+        cudaEventRecord(ea, 0);
+        bfs_expand_kernel<<<grid, warps_per_block * 32>>>(f->buf[cur_buf], f->buf[cur_buf ^ 1], f->stride,
+                                                          st.nodes[st.cur], (int)need, st.children);
+        bfs_compact_kernel<<<1, 1024>>>(st.nodes[st.cur], st.node_tree[st.cur], st.children, (int)need,
+                                        st.nodes[st.cur ^ 1], st.node_tree[st.cur ^ 1], st.tree_parent, st.tree_lit,
+                                        (int)st.tree_count, st.totals);
+        cudaEventRecord(eb, 0);
+        f->bfs_launches += 2;
+        BfsLevelTotals tot;
+        cudaError_t ce = cudaMemcpy(&tot, st.totals, sizeof tot, cudaMemcpyDeviceToHost);
         if (ce != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS level: ") + cudaGetErrorString(ce)); break; }
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev0, ev1);
-        f->bfs_kernel_ms += ms;
-        f->bfs_launches += 1;
-        f->h2d_bytes += need * sizeof(BfsNode);
+        f->d2h_bytes += sizeof tot;
+        if (safe) {
+            // every node of the level is expanded; only the totals matter
+            it += (long long)tot.expanded;
+            task_count += (long long)tot.m_next;
+            f->bfs_evals += tot.evals;
+            st.tree_count += tot.m_next;
+            st.cur ^= 1;
+            cur_buf ^= 1;
+            m = tot.m_next;
+            continue;
+        }
+        // a stop test can fire here: walk the level on the host with the exact rules
+        if ((status = st.download_level(m, h_nodes, h_node_tree, f->d2h_bytes))) break;
+        h_children.resize(2 * need);
+        ce = cudaMemcpy(h_children.data(), st.children, 2 * need * sizeof(BfsChild), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS level: ") + cudaGetErrorString(ce)); break; }
         f->d2h_bytes += 2 * need * sizeof(BfsChild);
-
-        next.clear();
-        size_t s = m;
+        std::vector<Entry> next_entries;
+        size_t s = m, E = 0;
         bool stopped = false;
         for (size_t j = 0; j < need; ++j) {
             if (Q > 0 && s >= (size_t)Q) { stopped = true; break; }  // NDP:894-895 before this pop
-            const HostNode& nd = cur[j];
+            const BfsNode& nd = h_nodes[j];
             const int var = nd.kind == K_UNIT ? std::abs(nd.lit) : nd.lit;
             E = j + 1;                                               // popped (NDP:898-899)
             s -= 1;
@@ -289,31 +384,45 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
             for (int b = 0; b < 2; ++b) {                            // LA then RA (NDP:904-925)
                 const BfsChild& c = h_children[2 * j + b];
                 if (c.n < 0) continue;
-                int32_t tree = (int32_t)f->tree_parent.size();
-                f->tree_parent.push_back(nd.tree);
-                f->tree_lit.push_back(b == 0 ? var : -var);
-                next.push_back(HostNode{(uint32_t)(2 * j + b), c.n, c.kind, c.lit, tree});
+                int32_t tree = (int32_t)(st.tree_count + host_tree_tail.size());
+                host_tree_tail.push_back(Pushed{h_node_tree[j], b == 0 ? var : -var});
+                next_entries.push_back(Entry{cur_buf ^ 1, (uint32_t)(2 * j + b), c.n, tree});
                 ++task_count;
                 ++s;
             }
             ++it;                                                    // NDP:926
             if (Q <= 0 && it >= D) { stopped = true; break; }        // NDP:935-936
         }
-        have_next = true;
-        if (stopped || E < m) break;
-        cur.swap(next);
+        if (stopped || E < m) {
+            // frontier = unexpanded rest of the current level, then the children pushed so far
+            for (size_t j = E; j < m; ++j) final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j]});
+            final_entries.insert(final_entries.end(), next_entries.begin(), next_entries.end());
+            done = true;
+            break;
+        }
+        // no stop fired: the device-side compaction of this level is exactly what the walk produced
+        host_tree_tail.clear();
+        st.tree_count += tot.m_next;
+        st.cur ^= 1;
         cur_buf ^= 1;
+        m = tot.m_next;
     }
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    if (d_nodes) cudaFree(d_nodes);
-    if (d_children) cudaFree(d_children);
+    cudaDeviceSynchronize();
+    for (size_t e = 0; e + 1 < evs.size(); e += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, evs[e], evs[e + 1]) == cudaSuccess) f->bfs_kernel_ms += ms;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (status) return status;
 
-    // frontier = unexpanded rest of the current level, then the children pushed so far
-    for (size_t j = E; j < cur.size(); ++j) f->entries.push_back(Entry{cur_buf, cur[j].slot, cur[j].n, cur[j].tree});
-    if (have_next)
-        for (const HostNode& c : next) f->entries.push_back(Entry{cur_buf ^ 1, c.slot, c.n, c.tree});
+    // bring the choice tree home (parent pointers + literals), then the stop level's tail
+    f->tree_parent.resize(st.tree_count);
+    f->tree_lit.resize(st.tree_count);
+    CUDA_TRY(cudaMemcpy(f->tree_parent.data(), st.tree_parent, st.tree_count * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(f->tree_lit.data(), st.tree_lit, st.tree_count * 4, cudaMemcpyDeviceToHost));
+    f->d2h_bytes += st.tree_count * 8;
+    for (const Pushed& p : host_tree_tail) { f->tree_parent.push_back(p.parent_tree); f->tree_lit.push_back(p.lit); }
+    f->entries.swap(final_entries);
 
     if (iterations_out) *iterations_out = (int)it;
     if (task_count_out) *task_count_out = (int)task_count;
@@ -439,7 +548,7 @@ int plan_dfs(int device, int n_max, int max_var, DfsLaunchPlan& plan) {
     CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     DfsParams& p = plan.p;
-    p.w_cap = std::max(n_max, 1);
+    p.w_cap = pad_up(std::max(n_max, 1));
     p.trail_cap = std::max(max_var, 1);
     p.table_words = (max_var + 1 + 15) / 16;
     p.pend_words = (p.trail_cap + 31) / 32;

@@ -53,6 +53,88 @@ __global__ void __launch_bounds__(256) bfs_expand_kernel(const pclause* __restri
     }
 }
 
+// After a level has been expanded: turn the per-child metadata into the next level's node
+// list, in queue order (children of node 0 first, LA before RA -- NDP:904-925), append the
+// pushed children to the choice tree, and reduce the level's counters.  One CTA walks the
+// 2m children with a block-wide exclusive scan of the "open" flags (warp ballots + a 32-entry
+// shared array), so the frontier is compacted without the host ever seeing it.
+struct BfsLevelTotals {
+    unsigned m_next;             // open children = size of the next level
+    unsigned expanded;           // nodes that count as an iteration (choice() != 0, NDP:901-902, 926)
+    unsigned long long evals;    // sum of |A| over those nodes
+    unsigned max_n;              // largest child
+    unsigned pad[3];
+};
+
+__global__ void __launch_bounds__(1024) bfs_compact_kernel(const BfsNode* __restrict__ nodes,
+                                                           const int32_t* __restrict__ node_tree,
+                                                           const BfsChild* __restrict__ children, int m,
+                                                           BfsNode* __restrict__ next_nodes,
+                                                           int32_t* __restrict__ next_tree,
+                                                           int32_t* __restrict__ tree_parent,
+                                                           int32_t* __restrict__ tree_lit, int tree_base,
+                                                           BfsLevelTotals* __restrict__ totals) {
+    __shared__ unsigned warp_count[32];
+    __shared__ unsigned long long red_evals[32];
+    __shared__ unsigned red_exp[32], red_max[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned lt = lanemask_lt();
+    unsigned running = 0;
+    unsigned long long evals = 0;
+    unsigned expanded = 0, max_n = 0;
+    for (int base = 0; base < 2 * m; base += 1024) {
+        const int idx = base + (int)tid;
+        BfsChild ch;
+        ch.n = -1;
+        if (idx < 2 * m) ch = children[idx];
+        const bool open = ch.n >= 0;
+        const unsigned bal = __ballot_sync(kFullMask, open);
+        if (lane == 0) warp_count[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const unsigned c = warp_count[w];
+            if (w < (int)warp) before += c;
+            total += c;
+        }
+        if (open) {
+            const int j = idx >> 1;
+            const BfsNode nd = nodes[j];
+            const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+            const unsigned pos = running + before + __popc(bal & lt);
+            BfsNode nn;
+            nn.slot = (uint32_t)idx;
+            nn.n = ch.n;
+            nn.kind = ch.kind;
+            nn.lit = ch.lit;
+            next_nodes[pos] = nn;
+            next_tree[pos] = tree_base + (int)pos;
+            tree_parent[tree_base + pos] = node_tree[j];
+            tree_lit[tree_base + pos] = (idx & 1) ? -var : var;
+            max_n = max(max_n, (unsigned)ch.n);
+        }
+        running += total;
+        __syncthreads();
+    }
+    for (int j = (int)tid; j < m; j += 1024) {
+        const BfsNode nd = nodes[j];
+        const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+        if (nd.n > 0 && var != 0) { evals += (unsigned long long)nd.n; ++expanded; }
+    }
+    for (int off = 16; off > 0; off >>= 1) evals += __shfl_down_sync(kFullMask, evals, off);
+    expanded = __reduce_add_sync(kFullMask, expanded);
+    max_n = __reduce_max_sync(kFullMask, max_n);
+    if (lane == 0) { red_evals[warp] = evals; red_exp[warp] = expanded; red_max[warp] = max_n; }
+    __syncthreads();
+    if (tid == 0) {
+        BfsLevelTotals t;
+        t.m_next = running; t.expanded = 0; t.evals = 0; t.max_n = 0;
+        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+        for (int w = 0; w < 32; ++w) { t.evals += red_evals[w]; t.expanded += red_exp[w]; t.max_n = max(t.max_n, red_max[w]); }
+        *totals = t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // DFS (Satisfy_iterative(A, true), NDP-5_6_7.cpp:784-878).  Persistent grid; every warp pulls
 // the next subproblem of its shard from an atomic counter and runs the whole search:
@@ -134,12 +216,12 @@ __global__ void dfs_kernel(const DfsParams p) {
                 // i = |x|: the branch that makes x false emits {0,0,0} (conflict, never pushed, NDP:837/857)
                 t = cur.lit;
             } else {
-                SetInfo la = warp_classify(W, n_buf, cur.n, var, sticky, lane);
+                SetInfo la = warp_pass_lazy<false>(W, n_buf, cur.n, var, sticky, lane);
                 if (la.n == 0) {                                 // LA empty wins before RA is looked at (NDP:843-850)
                     if (lane == 0) trail[ntrail] = (short)var;
                     ++ntrail; verdict = 1; break;
                 }
-                SetInfo ra = warp_classify(W, n_buf, cur.n, -var, sticky, lane);
+                SetInfo ra = warp_pass_lazy<false>(W, n_buf, cur.n, -var, sticky, lane);
                 if (ra.n == 0) {                                 // NDP:863-870
                     if (lane == 0) trail[ntrail] = (short)(-var);
                     ++ntrail; verdict = 1; break;
@@ -154,7 +236,7 @@ __global__ void dfs_kernel(const DfsParams p) {
                     trail[ntrail] = (short)t;
                 }
                 ++ntrail;
-                SetInfo r = warp_apply_lazy(W, n_buf, cur.n, t, sticky, lane);
+                SetInfo r = warp_pass_lazy<true>(W, n_buf, cur.n, t, sticky, lane);
                 __syncwarp();
                 if (r.n == 0) { verdict = 1; break; }           // empty branch => model (NDP:843-852 / 863-872)
                 if (r.conflict) dead = true;
