@@ -3,6 +3,7 @@
 // There is no CPU fallback in this file: every compute entry point needs a CUDA device.
 #include "../../include/ndp_b200.h"
 #include "ndp_kernels.cuh"
+#include "ndp_index.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -22,6 +23,7 @@ namespace {
 
 thread_local std::string g_err;
 thread_local int g_device = 0;
+int g_engine = NDP_ENGINE_AUTO;   // process-wide; ndp_set_engine / env NDP_ENGINE
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -88,6 +90,19 @@ struct ndp_frontier {
         int n_max = 0;
     };
     std::vector<Replica> replicas;
+    // index engine (BFS-born frontiers only): host copy of the root, device copy of the choice tree
+    bool has_root = false;
+    std::vector<int32_t> root_c3;
+    int32_t *d_tree_parent = nullptr, *d_tree_lit = nullptr;   // on `device`
+    struct IndexReplica {
+        int device = -1;
+        size_t first = 0, stride = 1, n_local = 0;
+        pclause* d_root = nullptr;
+        unsigned *d_occ_off = nullptr, *d_occ = nullptr;
+        unsigned* d_prefix_tables = nullptr;
+        int table_words = 0, n_zero3 = 0, first_zero3 = -1;
+    };
+    std::vector<IndexReplica> index_replicas;
 
     void choices_of(size_t k, std::vector<int32_t>& out) const {
         out.clear();
@@ -119,7 +134,16 @@ struct ndp_frontier {
     }
     ~ndp_frontier() {
         free_replicas();
+        for (auto& r : index_replicas) {
+            cudaSetDevice(r.device);
+            if (r.d_root) cudaFree(r.d_root);
+            if (r.d_occ_off) cudaFree(r.d_occ_off);
+            if (r.d_occ) cudaFree(r.d_occ);
+            if (r.d_prefix_tables) cudaFree(r.d_prefix_tables);
+        }
         cudaSetDevice(device);
+        if (d_tree_parent) cudaFree(d_tree_parent);
+        if (d_tree_lit) cudaFree(d_tree_lit);
         for (int b = 0; b < 2; ++b)
             if (buf[b]) cudaFree(buf[b]);
     }
@@ -231,6 +255,12 @@ const char* ndp_version(void) { return "ndp-b200 0.1 (NDP 5.6.7 hot path, sm_100
 int ndp_set_device(int device) {
     if (device < 0) return fail(NDP_E_INVALID, "negative device ordinal");
     g_device = device;
+    return NDP_OK;
+}
+int ndp_set_engine(int engine) {
+    if (engine != NDP_ENGINE_AUTO && engine != NDP_ENGINE_SCAN && engine != NDP_ENGINE_INDEX)
+        return fail(NDP_E_INVALID, "unknown engine");
+    g_engine = engine;
     return NDP_OK;
 }
 int ndp_device_count(int* count) {
@@ -423,6 +453,22 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     f->d2h_bytes += st.tree_count * 8;
     for (const Pushed& p : host_tree_tail) { f->tree_parent.push_back(p.parent_tree); f->tree_lit.push_back(p.lit); }
     f->entries.swap(final_entries);
+    // the index engine derives every subproblem from the root + its choices: keep the root and
+    // leave the tree on the device (completed with the stop level's tail)
+    f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
+    f->has_root = true;
+    if (!host_tree_tail.empty()) {
+        if ((status = st.reserve_tree(f->tree_parent.size()))) return status;
+        CUDA_TRY(cudaMemcpy(st.tree_parent + st.tree_count, f->tree_parent.data() + st.tree_count,
+                            host_tree_tail.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(st.tree_lit + st.tree_count, f->tree_lit.data() + st.tree_count,
+                            host_tree_tail.size() * 4, cudaMemcpyHostToDevice));
+        f->h2d_bytes += host_tree_tail.size() * 8;
+    }
+    f->d_tree_parent = st.tree_parent;
+    f->d_tree_lit = st.tree_lit;
+    st.tree_parent = nullptr;   // ownership moves to the frontier
+    st.tree_lit = nullptr;
 
     if (iterations_out) *iterations_out = (int)it;
     if (task_count_out) *task_count_out = (int)task_count;
@@ -625,25 +671,170 @@ struct DevBuf {  // tiny RAII for the per-call device outputs
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// ---- index engine ---------------------------------------------------------------------------
+
+bool engine_uses_index(const ndp_frontier* f) {
+    int e = g_engine;
+    if (e == NDP_ENGINE_AUTO) {
+        const char* s = getenv("NDP_ENGINE");
+        if (s && !strcmp(s, "scan")) e = NDP_ENGINE_SCAN;
+        else if (s && !strcmp(s, "index")) e = NDP_ENGINE_INDEX;
+    }
+    if (!f->has_root) return false;   // explicit clause sets (resume): no common root to index
+    return e != NDP_ENGINE_SCAN;
+}
+
+struct IndexLaunchPlan {
+    int warps_per_cta, ctas_per_sm, grid, smem_bytes;
+    IndexParams p;
+};
+
+int plan_index(int device, int n_root, int max_var, IndexLaunchPlan& plan) {
+    int sms = 0, smem_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    IndexParams& p = plan.p;
+    p.bm_words = (n_root + 31) / 32;
+    p.table_words = (max_var + 1 + 15) / 16;
+    p.trail_cap = std::max(max_var, 1);
+    p.pend_words = (p.trail_cap + 31) / 32;
+    size_t off = align16((size_t)3 * p.bm_words * 4);
+    p.off_table = (int)off; off += align16((size_t)p.table_words * 4);
+    p.off_pend = (int)off;  off += align16((size_t)p.pend_words * 4);
+    p.warp_bytes = (int)std::max(off, (size_t)16);
+    if ((size_t)p.warp_bytes > (size_t)smem_optin)
+        return fail(NDP_E_UNSUPPORTED, "clause count too large for the shared-memory bitmaps");
+    const int sm_smem = 233472;
+    int best_total = 0, best_w = 1, best_ctas = 1;
+    for (int w : {4, 2, 1}) {
+        size_t cta = (size_t)p.warp_bytes * w;
+        if (cta > (size_t)smem_optin) continue;
+        int ctas = (int)std::min<size_t>(32 / w, (size_t)sm_smem / (cta + 1024));
+        if (ctas < 1) continue;
+        if (w * ctas > best_total) { best_total = w * ctas; best_w = w; best_ctas = ctas; }
+    }
+    plan.warps_per_cta = best_w;
+    plan.ctas_per_sm = best_ctas;
+    plan.smem_bytes = p.warp_bytes * best_w;
+    plan.grid = sms * best_ctas;
+    return NDP_OK;
+}
+
+int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_frontier::IndexReplica** out) {
+    for (auto& r : f->index_replicas)
+        if (r.device == device && r.first == first && r.stride == stride) { *out = &r; return NDP_OK; }
+    ndp_frontier::IndexReplica r;
+    r.device = device;
+    r.first = first;
+    r.stride = stride;
+    const size_t total = f->entries.size();
+    r.n_local = first < total ? (total - first + stride - 1) / stride : 0;
+    const size_t n_root = f->root_c3.size() / 3;
+    const int V = f->max_var;
+    // root records + merged occurrence lists (c | n_pos << 24 | n_neg << 26), built on the host once
+    std::vector<pclause> root(std::max(n_root, (size_t)1));
+    std::vector<unsigned> off((size_t)V + 2, 0), occ;
+    if (n_root >= (1u << 24)) return fail(NDP_E_UNSUPPORTED, "more than 2^24 root clauses");
+    {
+        std::vector<std::vector<unsigned>> per_var((size_t)V + 1);
+        for (size_t c = 0; c < n_root; ++c) {
+            const int32_t* l = &f->root_c3[3 * c];
+            root[c] = pack_clause(l[0], l[1], l[2]);
+            if (!l[0] && !l[1] && !l[2]) { ++r.n_zero3; if (r.first_zero3 < 0) r.first_zero3 = (int)c; }
+            for (int j = 0; j < 3; ++j) {
+                if (!l[j]) continue;
+                bool seen = false;
+                for (int i = 0; i < j; ++i) seen |= l[i] && std::abs(l[i]) == std::abs(l[j]);
+                if (seen) continue;
+                unsigned n_pos = 0, n_neg = 0;
+                for (int i = 0; i < 3; ++i) {
+                    if (l[i] == std::abs(l[j])) ++n_pos;
+                    if (l[i] == -std::abs(l[j])) ++n_neg;
+                }
+                per_var[(size_t)std::abs(l[j])].push_back((unsigned)c | (n_pos << 24) | (n_neg << 26));
+            }
+        }
+        for (int v = 0; v <= V; ++v) {
+            off[v] = (unsigned)occ.size();
+            occ.insert(occ.end(), per_var[v].begin(), per_var[v].end());
+        }
+        off[(size_t)V + 1] = (unsigned)occ.size();
+    }
+    r.table_words = (V + 1 + 15) / 16;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(&r.d_root, root.size() * sizeof(pclause)));
+    CUDA_TRY(cudaMalloc(&r.d_occ_off, off.size() * 4));
+    CUDA_TRY(cudaMalloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
+    CUDA_TRY(cudaMemcpy(r.d_root, root.data(), root.size() * sizeof(pclause), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_occ_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    if (!occ.empty()) CUDA_TRY(cudaMemcpy(r.d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
+    f->h2d_bytes += root.size() * sizeof(pclause) + off.size() * 4 + occ.size() * 4;
+    // each subproblem's choices as a 2-bit assignment table, derived on the device from the tree
+    const size_t tbytes = std::max(r.n_local, (size_t)1) * r.table_words * 4;
+    CUDA_TRY(cudaMalloc(&r.d_prefix_tables, tbytes));
+    CUDA_TRY(cudaMemset(r.d_prefix_tables, 0, tbytes));
+    if (r.n_local) {
+        std::vector<int32_t> h_entry_tree(total);
+        for (size_t k = 0; k < total; ++k) h_entry_tree[k] = f->entries[k].tree;
+        DevBuf d_entry, d_tp, d_tl;
+        CUDA_TRY(cudaMalloc(&d_entry.p, total * 4));
+        CUDA_TRY(cudaMemcpy(d_entry.p, h_entry_tree.data(), total * 4, cudaMemcpyHostToDevice));
+        f->h2d_bytes += total * 4;
+        const int32_t *tp = f->d_tree_parent, *tl = f->d_tree_lit;
+        if (device != f->device || !tp) {   // another GPU: ship the tree from the host copy
+            const size_t tn = f->tree_parent.size();
+            CUDA_TRY(cudaMalloc(&d_tp.p, tn * 4));
+            CUDA_TRY(cudaMalloc(&d_tl.p, tn * 4));
+            CUDA_TRY(cudaMemcpy(d_tp.p, f->tree_parent.data(), tn * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_tl.p, f->tree_lit.data(), tn * 4, cudaMemcpyHostToDevice));
+            f->h2d_bytes += tn * 8;
+            tp = d_tp.as<int32_t>();
+            tl = d_tl.as<int32_t>();
+        }
+        const int threads = 128;
+        const int blocks = (int)std::min<size_t>((r.n_local + threads - 1) / threads, 4096);
+        prefix_table_kernel<<<blocks, threads>>>(d_entry.as<int32_t>(), tp, tl, first, stride, r.n_local,
+                                                 r.table_words, r.d_prefix_tables);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    f->index_replicas.push_back(r);
+    *out = &f->index_replicas.back();
+    return NDP_OK;
+}
+
 // One shard on one device.  `best_dev`/`peers`: early-exit words (this device's + peers').
 int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int early_exit,
                   unsigned long long* shared_best, unsigned long long* const* peer_best, int n_peers,
                   unsigned long long best_init, uint8_t* verdict, size_t* winner, std::vector<int32_t>* model,
                   uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
+    const bool use_index = engine_uses_index(f);
+    int rc;
     ndp_frontier::Replica* rep = nullptr;
-    int rc = build_replica(f, device, first, stride, &rep);
+    ndp_frontier::IndexReplica* irep = nullptr;
+    if (use_index) rc = build_index_replica(f, device, first, stride, &irep);
+    else rc = build_replica(f, device, first, stride, &rep);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
-    const size_t nl = rep->n_local;
+    const size_t nl = use_index ? irep->n_local : rep->n_local;
     if (winner) *winner = SIZE_MAX;
     if (nl == 0) return NDP_OK;
     if (nl > 0xfffffff0ull) return fail(NDP_E_UNSUPPORTED, "shard larger than the 32-bit work counter");
 
     DfsLaunchPlan plan;
-    if ((rc = plan_dfs(device, rep->n_max, f->max_var, plan))) return rc;
-    DfsParams& p = plan.p;
-    const int n_warps = plan.grid * plan.warps_per_cta;
-    p.model_stride = p.trail_cap;
+    IndexLaunchPlan iplan;
+    int n_warps, model_stride;
+    if (use_index) {
+        if ((rc = plan_index(device, (int)(f->root_c3.size() / 3), f->max_var, iplan))) return rc;
+        n_warps = iplan.grid * iplan.warps_per_cta;
+        model_stride = iplan.p.trail_cap;
+    } else {
+        if ((rc = plan_dfs(device, rep->n_max, f->max_var, plan))) return rc;
+        n_warps = plan.grid * plan.warps_per_cta;
+        plan.p.model_stride = plan.p.trail_cap;
+        model_stride = plan.p.model_stride;
+    }
 
     DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_msub, b_mlen, b_models, b_scratch;
     CUDA_TRY(cudaMalloc(&b_verdict.p, nl));
@@ -653,8 +844,9 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(cudaMalloc(&b_next.p, 4));
     CUDA_TRY(cudaMalloc(&b_msub.p, (size_t)n_warps * 8));
     CUDA_TRY(cudaMalloc(&b_mlen.p, (size_t)n_warps * 4));
-    CUDA_TRY(cudaMalloc(&b_models.p, (size_t)n_warps * p.model_stride * 4));
-    if (!plan.smem_w) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * p.w_cap * sizeof(pclause)));
+    CUDA_TRY(cudaMalloc(&b_models.p, (size_t)n_warps * model_stride * 4));
+    if (use_index) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
+    else if (!plan.smem_w) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * plan.p.w_cap * sizeof(pclause)));
     unsigned long long* d_best = shared_best;
     if (!d_best) {
         CUDA_TRY(cudaMalloc(&b_best.p, 8));
@@ -665,31 +857,60 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(cudaMemset(b_next.p, 0, 4));
     CUDA_TRY(cudaMemset(b_msub.p, 0xff, (size_t)n_warps * 8));
 
-    p.sub_base = rep->d_base;
-    p.sub_n = rep->d_n;
-    p.first = first; p.stride = stride; p.n_local = nl;
-    p.next = b_next.as<unsigned int>();
-    p.best = d_best;
-    p.n_peers = 0;
-    for (int d = 0; d < n_peers && d < 8; ++d)
-        if (peer_best[d] != d_best) p.peer_best[p.n_peers++] = peer_best[d];
-    p.early_exit = early_exit;
-    p.verdict = b_verdict.as<uint8_t>();
-    p.nodes = b_nodes.as<unsigned long long>();
-    p.evals = b_evals.as<unsigned long long>();
-    p.rebuilds = b_reb.as<unsigned int>();
-    p.model_sub = b_msub.as<unsigned long long>();
-    p.model_len = b_mlen.as<int32_t>();
-    p.models = b_models.as<int32_t>();
-    p.gscratch = b_scratch.as<pclause>();
-
     cudaEvent_t ev0, ev1;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
-    auto kern = plan.smem_w ? dfs_kernel<true> : dfs_kernel<false>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    CUDA_TRY(cudaEventRecord(ev0, 0));
-    kern<<<plan.grid, plan.warps_per_cta * 32, plan.smem_bytes>>>(p);
+    if (use_index) {
+        IndexParams& p = iplan.p;
+        p.root = irep->d_root;
+        p.n_root = (int)(f->root_c3.size() / 3);
+        p.occ_off = irep->d_occ_off;
+        p.occ = irep->d_occ;
+        p.prefix_tables = irep->d_prefix_tables;
+        p.n_zero3 = irep->n_zero3;
+        p.first_zero3 = irep->first_zero3;
+        p.first = first; p.stride = stride; p.n_local = nl;
+        p.next = b_next.as<unsigned int>();
+        p.best = d_best;
+        p.n_peers = 0;
+        for (int d = 0; d < n_peers && d < 8; ++d)
+            if (peer_best[d] != d_best) p.peer_best[p.n_peers++] = peer_best[d];
+        p.early_exit = early_exit;
+        p.verdict = b_verdict.as<uint8_t>();
+        p.nodes = b_nodes.as<unsigned long long>();
+        p.evals = b_evals.as<unsigned long long>();
+        p.rebuilds = b_reb.as<unsigned int>();
+        p.model_sub = b_msub.as<unsigned long long>();
+        p.model_len = b_mlen.as<int32_t>();
+        p.trails = b_scratch.as<short>();
+        p.models = b_models.as<int32_t>();
+        CUDA_TRY(cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
+        CUDA_TRY(cudaEventRecord(ev0, 0));
+        dfs_index_kernel<<<iplan.grid, iplan.warps_per_cta * 32, iplan.smem_bytes>>>(p);
+    } else {
+        DfsParams& p = plan.p;
+        p.sub_base = rep->d_base;
+        p.sub_n = rep->d_n;
+        p.first = first; p.stride = stride; p.n_local = nl;
+        p.next = b_next.as<unsigned int>();
+        p.best = d_best;
+        p.n_peers = 0;
+        for (int d = 0; d < n_peers && d < 8; ++d)
+            if (peer_best[d] != d_best) p.peer_best[p.n_peers++] = peer_best[d];
+        p.early_exit = early_exit;
+        p.verdict = b_verdict.as<uint8_t>();
+        p.nodes = b_nodes.as<unsigned long long>();
+        p.evals = b_evals.as<unsigned long long>();
+        p.rebuilds = b_reb.as<unsigned int>();
+        p.model_sub = b_msub.as<unsigned long long>();
+        p.model_len = b_mlen.as<int32_t>();
+        p.models = b_models.as<int32_t>();
+        p.gscratch = b_scratch.as<pclause>();
+        auto kern = plan.smem_w ? dfs_kernel<true> : dfs_kernel<false>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+        CUDA_TRY(cudaEventRecord(ev0, 0));
+        kern<<<plan.grid, plan.warps_per_cta * 32, plan.smem_bytes>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1, 0));
     CUDA_TRY(cudaEventSynchronize(ev1));
@@ -726,7 +947,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
             if (h_msub[w] == (unsigned long long)win) {
                 f->choices_of(win, *model);                       // choices_k ++ dfs choices (NDP:1430-1431)
                 std::vector<int32_t> tail((size_t)h_mlen[w]);
-                CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * p.model_stride,
+                CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * model_stride,
                                     tail.size() * 4, cudaMemcpyDeviceToHost));
                 model->insert(model->end(), tail.begin(), tail.end());
                 break;

@@ -1,0 +1,320 @@
+// ndp_index.cuh -- the occurrence-index DFS engine.
+//
+// Same search as dfs_kernel (ndp_kernels.cuh) -- the reference's Satisfy_iterative node for node
+// (NDP-5_6_7.cpp:784-878), same choices in the same order, same node and clause-evaluation
+// counts -- but a node no longer scans its clause set to find the ~dozen clauses that mention the
+// assigned variable.  All subproblems of a BFS frontier are the ROOT clause array filtered by an
+// assignment (SURVEY.md §8a equivalences), so one read-only index over the root serves them all:
+//
+//   root[c]      the packed root clause (ndp_clause.cuh record; zc = zeros it was parsed with)
+//   occ[v]       clauses that mention variable v, merged per clause: c | n_pos << 24 | n_neg << 26
+//                (n_pos / n_neg = how many of the clause's literals are +v / -v, so duplicate
+//                literals and tautologies need no special case)
+//
+// and a warp's whole search state is three bitmaps over root clause ids plus the assignment:
+//
+//   B[k] (k = 0,1,2)  clause is live and currently has exactly k zero literals
+//   table             2 bits per variable (0 unassigned, 1 true, 2 false)
+//   trail, pend       choices in decision order (global memory) and the pending-sibling bits
+//
+// choice() (NDP:753-781) becomes find-first-set: the first live two-zero clause is the lowest set
+// bit of B[2], the first one-zero clause that of B[1], A[0] that of B[0].  Resolution
+// (NDP:654-697) becomes: walk occ[v]; a clause holding the true literal leaves its bitmap
+// (satisfied, dropped); one holding only false literals moves from B[k] to B[k + n_false], and
+// reaching three zeros is the conflict.  A popped sibling is re-derived from the table with one
+// pass over the root (no stack of clause sets).
+#pragma once
+#include "ndp_clause.cuh"
+
+namespace ndp {
+
+struct IndexParams {
+    const pclause* root;              // [n_root]
+    int n_root;
+    const unsigned* occ_off;          // [max_var + 2]
+    const unsigned* occ;              // merged occurrence entries
+    const unsigned* prefix_tables;    // [n_local][table_words]: assignment of each subproblem's choices
+    int table_words, bm_words, pend_words, trail_cap;
+    int n_zero3;                      // root clauses that are {0,0,0} (never leave, always conflict)
+    int first_zero3;                  // lowest such index, or -1
+    unsigned long long first, stride, n_local;
+    unsigned int* next;
+    unsigned long long* best;
+    unsigned long long* peer_best[8];
+    int n_peers;
+    int early_exit;
+    uint8_t* verdict;
+    unsigned long long* nodes;
+    unsigned long long* evals;
+    unsigned int* rebuilds;
+    unsigned long long* model_sub;    // [n_warps]
+    int32_t* model_len;               // [n_warps]
+    short* trails;                    // [n_warps][trail_cap] working trail of each warp
+    int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
+    int warp_bytes, off_table, off_pend;   // shared-memory layout of one warp: B[3][bm_words], table, pend
+};
+
+// lowest set bit of a bitmap of `words` words, or -1
+__device__ __forceinline__ int bitmap_first(const unsigned* B, int words, unsigned lane) {
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        const int w = w0 + (int)lane;
+        const unsigned word = w < words ? B[w] : 0u;
+        const unsigned m = __ballot_sync(kFullMask, word != 0u);
+        if (m) {
+            const int src = __ffs(m) - 1;
+            const unsigned wd = __shfl_sync(kFullMask, word, src);
+            return (w0 + src) * 32 + __ffs(wd) - 1;
+        }
+    }
+    return -1;
+}
+
+// Derive the three bitmaps from the assignment table with one pass over the root.
+// Returns the number of live clauses (all-zero root clauses included: they are part of |A|).
+__device__ __noinline__ int index_rebuild(const IndexParams& p, unsigned* B, const unsigned* table, unsigned lane) {
+    int n_live = 0;
+    for (int base = 0; base < p.bm_words * 32; base += 32) {
+        const int c = base + (int)lane;
+        bool live = false;
+        unsigned zc = 0;
+        if (c < p.n_root) {
+            const pclause cl = __ldg(&p.root[c]);
+            const unsigned f[3] = {cl.x & 0xffffu, cl.x >> 16, cl.y & 0xffffu};
+            bool sat = false;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (f[j] == 0u) ++zc;
+                else {
+                    const unsigned val = table_get(table, f[j] >> 1);
+                    const unsigned truth = (f[j] & 1u) ? 2u : 1u;
+                    if (val == truth) sat = true;
+                    else if (val != 0u) ++zc;
+                }
+            }
+            live = !sat;
+        }
+        const unsigned b0 = __ballot_sync(kFullMask, live && zc == 0u);
+        const unsigned b1 = __ballot_sync(kFullMask, live && zc == 1u);
+        const unsigned b2 = __ballot_sync(kFullMask, live && zc == 2u);
+        const unsigned b3 = __ballot_sync(kFullMask, live && zc == 3u);
+        if (lane == 0) {
+            const int w = base >> 5;
+            B[w] = b0;
+            B[p.bm_words + w] = b1;
+            B[2 * p.bm_words + w] = b2;
+        }
+        n_live += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+    }
+    __syncwarp();
+    return n_live;
+}
+
+// What choice() returns for the current state: kind/lit as in SetInfo.
+__device__ __forceinline__ void index_choice(const IndexParams& p, const unsigned* B, const unsigned* table, int n_live,
+                                             unsigned lane, int& kind, int& lit) {
+    if (n_live == 0) { kind = K_EMPTY; lit = 0; return; }
+    int c = bitmap_first(B + 2 * p.bm_words, p.bm_words, lane);
+    const bool unit = c >= 0;
+    if (!unit) c = bitmap_first(B + p.bm_words, p.bm_words, lane);
+    if (c >= 0) {
+        // the clause's literals that are still there (non-zero and unassigned); take the LAST one
+        const pclause cl = __ldg(&p.root[c]);
+        const unsigned f = lane == 0 ? (cl.x & 0xffffu) : lane == 1 ? (cl.x >> 16) : (cl.y & 0xffffu);
+        const bool there = lane < 3 && f != 0u && table_get(table, f >> 1) == 0u;
+        const unsigned m = __ballot_sync(kFullMask, there);
+        const int src = 31 - __clz((int)m);
+        const int l = code_lit(__shfl_sync(kFullMask, f, src));
+        if (unit) { kind = K_UNIT; lit = l; }
+        else { kind = K_DECIDE; lit = l < 0 ? -l : l; }
+        return;
+    }
+    // neither units nor one-zero clauses: |A[0].l[0]| (NDP:778-779)
+    c = bitmap_first(B, p.bm_words, lane);
+    kind = K_DECIDE;
+    if (p.first_zero3 >= 0 && (c < 0 || p.first_zero3 < c)) { lit = 0; return; }   // A[0] is {0,0,0}
+    const int l = code_lit(__ldg(&p.root[c]).x & 0xffffu);
+    lit = l < 0 ? -l : l;
+}
+
+// Resolution for "literal t becomes true".  kWrite applies it; otherwise it only classifies.
+// Returns the live count afterwards; conflict is raised when a clause reaches three zeros.
+template <bool kWrite>
+__device__ __forceinline__ int index_assign(const IndexParams& p, unsigned* B, int n_live, int t, bool& conflict,
+                                            unsigned lane) {
+    const unsigned v = (unsigned)(t < 0 ? -t : t);
+    const unsigned a = __ldg(&p.occ_off[v]), b = __ldg(&p.occ_off[v + 1]);
+    int dropped = 0;
+    bool confl = false;
+    for (unsigned i = a + lane; i < b; i += 32) {
+        const unsigned e = __ldg(&p.occ[i]);
+        const unsigned c = e & 0xffffffu, n_pos = (e >> 24) & 3u, n_neg = (e >> 26) & 3u;
+        const unsigned w = c >> 5, bit = 1u << (c & 31u);
+        int k = -1;
+        if (B[w] & bit) k = 0;
+        else if (B[p.bm_words + w] & bit) k = 1;
+        else if (B[2 * p.bm_words + w] & bit) k = 2;
+        if (k < 0) continue;   // already satisfied earlier on this path
+        const unsigned n_true = t > 0 ? n_pos : n_neg, n_false = t > 0 ? n_neg : n_pos;
+        if (n_true) {
+            ++dropped;
+            if (kWrite) atomicAnd(&B[k * p.bm_words + w], ~bit);
+        } else {
+            const int k2 = k + (int)n_false;
+            if (k2 >= 3) confl = true;
+            if (kWrite) {
+                atomicAnd(&B[k * p.bm_words + w], ~bit);
+                if (k2 < 3) atomicOr(&B[k2 * p.bm_words + w], bit);
+            }
+        }
+    }
+    conflict = p.n_zero3 > 0 || __any_sync(kFullMask, confl);
+    if (kWrite) __syncwarp();
+    return n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
+}
+
+__global__ void dfs_index_kernel(const IndexParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    const unsigned gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned char* mine = smem_raw + (size_t)warp * p.warp_bytes;
+    unsigned* B = reinterpret_cast<unsigned*>(mine);
+    unsigned* table = reinterpret_cast<unsigned*>(mine + p.off_table);
+    unsigned* pend = reinterpret_cast<unsigned*>(mine + p.off_pend);
+    short* trail = p.trails + (size_t)gwarp * p.trail_cap;
+
+    for (;;) {
+        unsigned q = 0;
+        if (lane == 0) q = atomicAdd(p.next, 1u);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= p.n_local) break;
+        const unsigned long long g = p.first + (unsigned long long)q * p.stride;
+        if (p.early_exit && *(volatile unsigned long long*)p.best < g) {
+            if (lane == 0) { p.verdict[q] = 2; p.nodes[q] = 0; p.evals[q] = 0; p.rebuilds[q] = 0; }
+            continue;
+        }
+        const unsigned* ptab = p.prefix_tables + (size_t)q * p.table_words;
+        for (int w = lane; w < p.table_words; w += 32) table[w] = __ldg(&ptab[w]);
+        for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
+        __syncwarp();
+        int n_live = index_rebuild(p, B, table, lane);
+        int kind, lit;
+        index_choice(p, B, table, n_live, lane, kind, lit);
+        int ntrail = 0;
+        unsigned long long nodes = 0, evals = 0;
+        unsigned rebuilds = 0;
+        int verdict = 0;
+        for (;;) {
+            ++nodes;  // one Satisfy_iterative loop iteration (NDP:801-806)
+            if (p.early_exit && (nodes & 63u) == 0 && *(volatile unsigned long long*)p.best < g) { verdict = 2; break; }
+            const int var = kind == K_UNIT ? (lit < 0 ? -lit : lit) : lit;
+            if (n_live == 0 || var == 0) { verdict = 1; break; }   // choice()==0: record choices (NDP:817-823)
+            evals += (unsigned long long)n_live;                   // one ResolutionStepWithConflict (NDP:831)
+            int t = 0;
+            bool pending = false;
+            if (kind == K_UNIT) {
+                t = lit;   // the other branch falsifies the unit clause: {0,0,0}, never pushed
+            } else {
+                bool la_conf, ra_conf;
+                const int la_n = index_assign<false>(p, B, n_live, var, la_conf, lane);
+                if (la_n == 0) {                                    // LA empty wins first (NDP:843-850)
+                    if (lane == 0) trail[ntrail] = (short)var;
+                    ++ntrail; verdict = 1; break;
+                }
+                const int ra_n = index_assign<false>(p, B, n_live, -var, ra_conf, lane);
+                if (ra_n == 0) {                                    // NDP:863-870
+                    if (lane == 0) trail[ntrail] = (short)(-var);
+                    ++ntrail; verdict = 1; break;
+                }
+                if (!ra_conf) { t = -var; pending = !la_conf; }     // RA is explored first
+                else if (!la_conf) t = var;
+            }
+            bool dead = t == 0;
+            if (!dead) {
+                if (lane == 0) {
+                    if (pending) pend[ntrail >> 5] |= 1u << (ntrail & 31);
+                    trail[ntrail] = (short)t;
+                    const unsigned v = (unsigned)(t < 0 ? -t : t);
+                    table[v >> 4] |= (t > 0 ? 1u : 2u) << ((v & 15u) * 2u);
+                }
+                ++ntrail;
+                bool conflict;
+                n_live = index_assign<true>(p, B, n_live, t, conflict, lane);
+                if (n_live == 0) { verdict = 1; break; }            // empty branch => model (NDP:843-852 / 863-872)
+                if (conflict) dead = true;
+                else { index_choice(p, B, table, n_live, lane, kind, lit); continue; }
+            }
+            // Backtrack: pop to the deepest decision whose LA sibling is still pending.
+            __syncwarp();
+            int pos = -1;
+            for (int w = (ntrail - 1) >> 5; w >= 0 && ntrail > 0; --w) {
+                unsigned bits = pend[w];
+                if (w == ((ntrail - 1) >> 5)) {
+                    const int top = (ntrail - 1) & 31;
+                    if (top != 31) bits &= (2u << top) - 1u;
+                }
+                if (bits) { pos = w * 32 + 31 - __clz(bits); break; }
+            }
+            if (pos < 0) break;   // stack empty: UNSAT
+            __syncwarp();
+            if (lane == 0) {
+                pend[pos >> 5] &= ~(1u << (pos & 31));
+                trail[pos] = (short)(-trail[pos]);   // -i -> +i : now the LA sibling
+            }
+            ntrail = pos + 1;
+            for (int w = lane; w < p.table_words; w += 32) table[w] = __ldg(&ptab[w]);
+            __syncwarp();
+            __threadfence_block();
+            for (int j = lane; j < ntrail; j += 32) {
+                const int l = trail[j];
+                const unsigned v = (unsigned)(l < 0 ? -l : l);
+                atomicOr(&table[v >> 4], (l > 0 ? 1u : 2u) << ((v & 15u) * 2u));
+            }
+            __syncwarp();
+            n_live = index_rebuild(p, B, table, lane);
+            index_choice(p, B, table, n_live, lane, kind, lit);
+            ++rebuilds;
+        }
+        if (verdict == 1) {
+            unsigned long long old = ~0ull;
+            if (lane == 0) {
+                old = atomicMin(p.best, g);
+                if (g < old)
+                    for (int d = 0; d < p.n_peers; ++d) atomicMin_system(p.peer_best[d], g);
+            }
+            old = __shfl_sync(kFullMask, old, 0);
+            if (g < old) {   // this warp now holds the lowest-index model: park it in its slot
+                __syncwarp();
+                __threadfence_block();
+                int32_t* out = p.models + (size_t)gwarp * p.trail_cap;
+                for (int j = lane; j < ntrail; j += 32) out[j] = (int32_t)trail[j];
+                if (lane == 0) { p.model_sub[gwarp] = g; p.model_len[gwarp] = ntrail; }
+            }
+        }
+        if (lane == 0) {
+            p.verdict[q] = (uint8_t)verdict;
+            p.nodes[q] = nodes;
+            p.evals[q] = evals;
+            p.rebuilds[q] = rebuilds;
+        }
+        __syncwarp();
+    }
+}
+
+// One thread per subproblem: walk its choices up the BFS tree and set them in its table row.
+__global__ void prefix_table_kernel(const int32_t* __restrict__ entry_tree, const int32_t* __restrict__ tree_parent,
+                                    const int32_t* __restrict__ tree_lit, unsigned long long first,
+                                    unsigned long long stride, unsigned long long n_local, int table_words,
+                                    unsigned* __restrict__ tables) {
+    for (unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; q < n_local;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned* row = tables + q * table_words;
+        for (int32_t t = entry_tree[first + q * stride]; t > 0; t = tree_parent[t]) {
+            const int l = tree_lit[t];
+            const unsigned v = (unsigned)(l < 0 ? -l : l);
+            row[v >> 4] |= (l > 0 ? 1u : 2u) << ((v & 15u) * 2u);
+        }
+    }
+}
+
+}  // namespace ndp

@@ -47,6 +47,7 @@ def _load():
     sig = {
         "ndp_set_device": (C.c_int, [C.c_int]),
         "ndp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+        "ndp_set_engine": (C.c_int, [C.c_int]),
         "ndp_last_error": (C.c_char_p, []),
         "ndp_version": (C.c_char_p, []),
         "ndp_bfs": (C.c_int, [_i32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -80,6 +81,15 @@ def _check(rc):
 
 def set_device(d):
     _check(lib.ndp_set_device(int(d)))
+
+
+ENGINE_AUTO, ENGINE_SCAN, ENGINE_INDEX = 0, 1, 2
+
+
+def set_engine(e):
+    """0 auto, 1 scan, 2 index (or the names)."""
+    e = {"auto": 0, "scan": 1, "index": 2}.get(e, e)
+    _check(lib.ndp_set_engine(int(e)))
 
 
 def device_count():

@@ -11,11 +11,14 @@ import util_cnf
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def nd():
+@pytest.fixture(scope="module", params=["index", "scan"])
+def nd(request):
+    """Every parity test runs once per DFS engine: both must match the oracle bit for bit."""
     import ndp5_b200
     assert ndp5_b200.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
-    return ndp5_b200
+    ndp5_b200.set_engine(request.param)
+    yield ndp5_b200
+    ndp5_b200.set_engine("auto")
 
 
 def gpu_frontier_list(fr):
