@@ -707,10 +707,12 @@ int plan_index(int device, int n_root, int max_var, IndexLaunchPlan& plan) {
         return fail(NDP_E_UNSUPPORTED, "clause count too large for the shared-memory bitmaps");
     const int sm_smem = 233472;
     int best_total = 0, best_w = 1, best_ctas = 1;
+    int cap_warps = 32;   // resident warps per SM; tunable for experiments
+    if (const char* s = getenv("NDP_INDEX_WARPS_PER_SM")) cap_warps = std::max(1, std::min(64, atoi(s)));
     for (int w : {4, 2, 1}) {
         size_t cta = (size_t)p.warp_bytes * w;
         if (cta > (size_t)smem_optin) continue;
-        int ctas = (int)std::min<size_t>(32 / w, (size_t)sm_smem / (cta + 1024));
+        int ctas = (int)std::min<size_t>(cap_warps / w, (size_t)sm_smem / (cta + 1024));
         if (ctas < 1) continue;
         if (w * ctas > best_total) { best_total = w * ctas; best_w = w; best_ctas = ctas; }
     }
@@ -885,6 +887,12 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.trails = b_scratch.as<short>();
         p.models = b_models.as<int32_t>();
         CUDA_TRY(cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
+        {
+            // leave L1 everything the resident CTAs do not need: the root index is read through it
+            const size_t need = (size_t)iplan.ctas_per_sm * (iplan.smem_bytes + 1024);
+            int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
+            cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
         CUDA_TRY(cudaEventRecord(ev0, 0));
         dfs_index_kernel<<<iplan.grid, iplan.warps_per_cta * 32, iplan.smem_bytes>>>(p);
     } else {

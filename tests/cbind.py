@@ -285,3 +285,148 @@ class RefLib(_Common):
           script.encode(), filename.encode(), cli_flag.encode(), outdir.encode(), iterations, initial_queue_size,
           world_rank, world_size, final_queue_size, buf, 1 << 20)
         return buf.value.decode()
+
+
+class HostLib:
+    """ctypes view of ndp-5_b200/lib/libndp_host.so (the C++17 host drop-in's test hooks)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(ROOT, "ndp-5_b200", "lib", "libndp_host.so"))
+
+    def _fn(self, name, restype, argtypes):
+        f = getattr(self.lib, "ndph_" + name)
+        f.restype = restype
+        f.argtypes = argtypes
+        return f
+
+    def _str(self, name, argtypes, *args):
+        f = self._fn(name, C.c_size_t, argtypes + [C.c_char_p, C.c_size_t])
+        buf = C.create_string_buffer(1 << 16)
+        f(*args, buf, 1 << 16)
+        return buf.value.decode()
+
+    def parse(self, text):
+        f = self._fn("parse_dimacs", C.c_size_t, [C.c_char_p, _i32p, C.c_size_t])
+        b = text.encode() if isinstance(text, str) else text
+        n = f(b, None, 0)
+        out = np.zeros((n, 3), dtype=np.int32)
+        if n:
+            f(b, out.ctypes.data_as(_i32p), n)
+        return out
+
+    def scrape_header(self, text):
+        f = self._fn("scrape_header", C.c_int, [C.c_char_p, _ip, _ip, _ip, C.c_char_p, C.c_size_t, _i32p, _szp,
+                                                _i32p, _szp, C.c_size_t])
+        nv, nc, nb = C.c_int(0), C.c_int(0), C.c_int(0)
+        prod = C.create_string_buffer(4096)
+        v1 = np.zeros(4096, dtype=np.int32)
+        v2 = np.zeros(4096, dtype=np.int32)
+        n1, n2 = C.c_size_t(0), C.c_size_t(0)
+        rc = f(text.encode(), C.byref(nv), C.byref(nc), C.byref(nb), prod, 4096, v1.ctypes.data_as(_i32p),
+               C.byref(n1), v2.ctypes.data_as(_i32p), C.byref(n2), 4096)
+        return dict(rc=rc, num_vars=nv.value, num_clauses=nc.value, num_bits=nb.value, product=prod.value.decode(),
+                    v1=v1[:n1.value].copy(), v2=v2[:n2.value].copy())
+
+    def calculate_max_iterations(self, world, clauses, nvars, bits):
+        return self._fn("calculate_max_iterations", C.c_int, [C.c_int] * 4)(world, clauses, nvars, bits)
+
+    def create_problem_id(self, n, bits, world, utc):
+        return self._str("create_problem_id", [C.c_char_p, C.c_int, C.c_int, C.c_char_p], n.encode(), bits, world,
+                         utc.encode())
+
+    def format_filename(self, script, file, pid, flag):
+        return self._str("format_filename", [C.c_char_p] * 4, script.encode(), file.encode(), pid.encode(),
+                         flag.encode())
+
+    def create_bfs_filename(self, script, file, pid, flag):
+        return self._str("create_bfs_filename", [C.c_char_p] * 4, script.encode(), file.encode(), pid.encode(),
+                         flag.encode())
+
+    def format_duration(self, s):
+        return self._str("format_duration", [C.c_double], float(s))
+
+    def format_percentage(self, a, b):
+        return self._str("format_percentage", [C.c_double, C.c_double], float(a), float(b))
+
+    def format_vector(self, v):
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.int32))
+        return self._str("format_vector", [_i32p, C.c_size_t], a.ctypes.data_as(_i32p), a.size)
+
+    def convert(self, model, v1, v2, input_number):
+        f = self._fn("convert", C.c_int, [_i32p, C.c_size_t, _i32p, C.c_size_t, _i32p, C.c_size_t, C.c_char_p,
+                                          C.c_char_p, C.c_char_p, C.c_size_t])
+        m = np.ascontiguousarray(np.asarray(model, dtype=np.int32))
+        a = np.ascontiguousarray(np.asarray(v1, dtype=np.int32))
+        b = np.ascontiguousarray(np.asarray(v2, dtype=np.int32))
+        d1 = C.create_string_buffer(4096)
+        d2 = C.create_string_buffer(4096)
+        ok = f(m.ctypes.data_as(_i32p), m.size, a.ctypes.data_as(_i32p), a.size, b.ctypes.data_as(_i32p), b.size,
+               str(input_number).encode(), d1, d2, 4096)
+        return int(d1.value), int(d2.value), bool(ok)
+
+    def parse_cli(self, args):
+        f = self._fn("parse_cli", C.c_int, [C.c_int, C.POINTER(C.c_char_p), _ip, _ip, C.c_char_p, C.c_size_t, _ip, _ip,
+                                            _ip, C.c_char_p, C.c_size_t, _ip, _ip, C.c_char_p, C.c_size_t])
+        argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        save, resume, mq, depth, ovr, gpus, exh = (C.c_int(0) for _ in range(7))
+        rf = C.create_string_buffer(4096)
+        flag = C.create_string_buffer(256)
+        err = C.create_string_buffer(4096)
+        rc = f(len(args), argv, C.byref(save), C.byref(resume), rf, 4096, C.byref(mq), C.byref(depth), C.byref(ovr),
+               flag, 256, C.byref(gpus), C.byref(exh), err, 4096)
+        return dict(rc=rc, save=bool(save.value), resume=bool(resume.value), resume_file=rf.value.decode(),
+                    max_queues=mq.value, depth=depth.value, override=bool(ovr.value), cli_flag=flag.value.decode(),
+                    gpus=gpus.value, exhaustive=bool(exh.value), error=err.value.decode())
+
+    def write_bfs_json(self, path, items, bfs_time):
+        f = self._fn("write_bfs_json", C.c_int, [C.c_char_p, _i32p, _szp, _i32p, _szp, C.c_size_t, C.c_double])
+        cl_off, ch_off = [0], [0]
+        for cl, ch in items:
+            cl_off.append(cl_off[-1] + len(cl))
+            ch_off.append(ch_off[-1] + len(ch))
+        cl_all = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32).reshape(-1, 3) for c, _ in items])
+                                      if items else np.zeros((0, 3), np.int32))
+        ch_all = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32).reshape(-1) for _, c in items])
+                                      if items else np.zeros(0, np.int32))
+        clo, cho = np.asarray(cl_off, dtype=np.uintp), np.asarray(ch_off, dtype=np.uintp)
+        return f(path.encode(), cl_all.ctypes.data_as(_i32p), clo.ctypes.data_as(_szp), ch_all.ctypes.data_as(_i32p),
+                 cho.ctypes.data_as(_szp), len(items), float(bfs_time))
+
+    def read_bfs_json(self, path):
+        rd = self._fn("read_bfs_json", C.c_void_p, [C.c_char_p])
+        h = rd(path.encode())
+        if not h:
+            return None
+        cnt = self._fn("json_count", C.c_size_t, [C.c_void_p])(h)
+        t = self._fn("json_time", C.c_double, [C.c_void_p])(h)
+        ncl = self._fn("json_nclauses", C.c_size_t, [C.c_void_p, C.c_size_t])
+        nch = self._fn("json_nchoices", C.c_size_t, [C.c_void_p, C.c_size_t])
+        cp = self._fn("json_copy", None, [C.c_void_p, C.c_size_t, _i32p, _i32p])
+        items = []
+        for k in range(cnt):
+            cl = np.zeros((ncl(h, k), 3), dtype=np.int32)
+            ch = np.zeros(nch(h, k), dtype=np.int32)
+            cp(h, k, cl.ctypes.data_as(_i32p), ch.ctypes.data_as(_i32p))
+            items.append((cl, ch))
+        self._fn("json_free", None, [C.c_void_p])(h)
+        return items, t
+
+    def report(self, solution_found, model, bfs_s, dfs_s, num_bits, num_vars, num_clauses, input_number, v1, v2,
+               script, filename, cli_flag, iterations, initial_queue_size, world_rank, world_size, final_queue_size,
+               utc):
+        f = self._fn("report", C.c_size_t,
+                     [C.c_int, _i32p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, _i32p,
+                      C.c_size_t, _i32p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_size_t, C.c_int,
+                      C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p,
+                      C.c_size_t])
+        m = np.ascontiguousarray(np.asarray(model, dtype=np.int32))
+        a = np.ascontiguousarray(np.asarray(v1, dtype=np.int32))
+        b = np.ascontiguousarray(np.asarray(v2, dtype=np.int32))
+        out = C.create_string_buffer(1 << 20)
+        ft = C.create_string_buffer(1 << 20)
+        fn = C.create_string_buffer(4096)
+        f(int(solution_found), m.ctypes.data_as(_i32p), m.size, bfs_s, dfs_s, num_bits, num_vars, num_clauses,
+          str(input_number).encode(), a.ctypes.data_as(_i32p), a.size, b.ctypes.data_as(_i32p), b.size,
+          script.encode(), filename.encode(), cli_flag.encode(), iterations, initial_queue_size, world_rank,
+          world_size, final_queue_size, utc.encode() if utc else None, out, 1 << 20, ft, 1 << 20, fn, 4096)
+        return out.value.decode(), ft.value.decode(), fn.value.decode()
