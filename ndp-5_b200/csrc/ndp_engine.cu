@@ -1,11 +1,16 @@
-// ndp_engine.cu -- host side of the C ABI (include/ndp_b200.h): device arena, BFS level
+// ndp_engine.cu -- host side of the C ABI (include/ndp_b200.h): device arenas, the BFS level
 // driver with the reference's exact -d/-q stop rules, DFS launch, result gather.
+// Two complete pipelines share the driver (ndp_set_engine / env NDP_ENGINE):
+//   scan  : nodes are clause sets (8-byte records) in fixed-stride slots; kernels in ndp_kernels.cuh
+//   index : nodes are state slots (3 bitmaps + assignment table) over one occurrence index of the
+//           root; kernels in ndp_index.cuh; clause lists are materialised on demand
 // There is no CPU fallback in this file: every compute entry point needs a CUDA device.
 #include "../../include/ndp_b200.h"
 #include "ndp_kernels.cuh"
 #include "ndp_index.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -37,11 +42,22 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
     } while (0)
 
+int requested_engine() {
+    int e = g_engine;
+    if (e == NDP_ENGINE_AUTO) {
+        const char* s = getenv("NDP_ENGINE");
+        if (s && !strcmp(s, "scan")) e = NDP_ENGINE_SCAN;
+        else if (s && !strcmp(s, "index")) e = NDP_ENGINE_INDEX;
+    }
+    return e;
+}
+
 struct Entry {        // one frontier element
-    int buf;          // arena buffer holding its clause slot
+    int buf;          // which of the two arena buffers holds its slot
     uint32_t slot;
-    int32_t n;
+    int32_t n;        // clauses in its set
     int32_t tree;     // index into the choice tree (BFS frontiers) or -1
+    int32_t kind, lit;   // what choice() returns for it (state frontiers)
 };
 
 // What choice() (NDP-5_6_7.cpp:753-781) says about a host clause array: same encoding as SetInfo.
@@ -60,49 +76,81 @@ void host_setinfo(const int32_t* c3, size_t n, int& kind, int& lit) {
     lit = v < 0 ? -v : v;
 }
 
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+bool tracing() { static const bool t = getenv("NDP_TRACE") != nullptr; return t; }
+
+struct DevBuf {  // tiny RAII for per-call device allocations
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
 }  // namespace
 
 struct ndp_frontier {
     int device = 0;
-    pclause* buf[2] = {nullptr, nullptr};   // the arena: two buffers of fixed-stride clause slots
-    size_t cap_slots[2] = {0, 0};
-    size_t stride = 0;                      // clauses per slot
     int max_var = 0;
     std::vector<Entry> entries;
-    // choices: either a parent-pointer tree (BFS) or flat arrays (resume)
+    // ---- clause-slot arena (scan pipeline; also the target of bulk materialisation)
+    pclause* buf[2] = {nullptr, nullptr};
+    size_t cap_slots[2] = {0, 0};
+    size_t stride = 0;                      // clauses per slot
+    // ---- state-slot arena (index pipeline)
+    bool states = false;                    // entries reference sbuf slots
+    unsigned* sbuf[2] = {nullptr, nullptr};
+    size_t scap_slots[2] = {0, 0};
+    bool materialised = false;              // buf[0] slot k holds entry k's clause list
+    // ---- choices: either a parent-pointer tree (BFS) or flat arrays (resume)
     std::vector<int32_t> tree_parent, tree_lit;
     std::vector<int32_t> flat_choices;
     std::vector<size_t> flat_off;
-    // BFS stats
+    int32_t *d_tree_parent = nullptr, *d_tree_lit = nullptr;   // device copy of the tree (on `device`)
+    size_t d_tree_count = 0;
+    bool host_tree_ready = true;            // false while the tree lives only on the device
+    // ---- root (BFS-born frontiers): what the index engine is built over
+    bool has_root = false;
+    std::vector<int32_t> root_c3;
+    struct RootIndex {                      // per device
+        int device = -1;
+        pclause* d_root = nullptr;
+        unsigned *d_occ_off = nullptr, *d_occ = nullptr;
+        IndexRoot ix;
+    };
+    std::vector<RootIndex> root_indexes;
+    // ---- stats
     uint64_t bfs_evals = 0, bfs_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     double bfs_kernel_ms = 0;
-    // scratch for ndp_frontier_get
+    // ---- scratch for ndp_frontier_get
     std::vector<int32_t> get_clauses, get_choices;
     std::vector<pclause> get_packed;
-    // per-device DFS descriptors (built lazily): index = device ordinal position in `replicas`
-    struct Replica {
+    pclause* d_get = nullptr;
+    const unsigned** d_get_ptr = nullptr;
+    // ---- per-(device, shard) DFS descriptors, built lazily
+    struct Replica {                        // scan DFS
         int device = -1;
-        size_t first = 0, stride = 1;        // the shard this replica serves
-        pclause* shard_buf = nullptr;        // private copy of the shard's slots (other devices only)
-        const pclause** d_base = nullptr;    // [n_local]
-        int32_t* d_n = nullptr;              // [n_local]
-        size_t n_local = 0;
+        size_t first = 0, stride = 1, n_local = 0;
+        pclause* shard_buf = nullptr;       // private copy of the shard's slots (other devices only)
+        const pclause** d_base = nullptr;   // [n_local]
+        int32_t* d_n = nullptr;             // [n_local]
         int n_max = 0;
     };
     std::vector<Replica> replicas;
-    // index engine (BFS-born frontiers only): host copy of the root, device copy of the choice tree
-    bool has_root = false;
-    std::vector<int32_t> root_c3;
-    int32_t *d_tree_parent = nullptr, *d_tree_lit = nullptr;   // on `device`
-    struct IndexReplica {
+    struct IndexReplica {                   // index DFS
         int device = -1;
         size_t first = 0, stride = 1, n_local = 0;
-        pclause* d_root = nullptr;
-        unsigned *d_occ_off = nullptr, *d_occ = nullptr;
-        unsigned* d_prefix_tables = nullptr;
-        int table_words = 0, n_zero3 = 0, first_zero3 = -1;
+        unsigned* own_slots = nullptr;      // state slots built or copied for this shard (else BFS slots are used)
+        const unsigned** d_slot_ptr = nullptr;   // [n_local]
+        BfsNode* d_meta = nullptr;          // [n_local]
     };
     std::vector<IndexReplica> index_replicas;
+
+    ndp_frontier() {   // pointers into these vectors are handed out: never reallocate them
+        root_indexes.reserve(16);
+        replicas.reserve(128);
+        index_replicas.reserve(128);
+    }
 
     void choices_of(size_t k, std::vector<int32_t>& out) const {
         out.clear();
@@ -123,29 +171,34 @@ struct ndp_frontier {
         }
         return flat_off.empty() ? 0 : flat_off[k + 1] - flat_off[k];
     }
-    void free_replicas() {
+    ~ndp_frontier() {
         for (auto& r : replicas) {
             cudaSetDevice(r.device);
             if (r.shard_buf) cudaFree(r.shard_buf);
             if (r.d_base) cudaFree((void*)r.d_base);
             if (r.d_n) cudaFree(r.d_n);
         }
-        replicas.clear();
-    }
-    ~ndp_frontier() {
-        free_replicas();
         for (auto& r : index_replicas) {
+            cudaSetDevice(r.device);
+            if (r.own_slots) cudaFree(r.own_slots);
+            if (r.d_slot_ptr) cudaFree((void*)r.d_slot_ptr);
+            if (r.d_meta) cudaFree(r.d_meta);
+        }
+        for (auto& r : root_indexes) {
             cudaSetDevice(r.device);
             if (r.d_root) cudaFree(r.d_root);
             if (r.d_occ_off) cudaFree(r.d_occ_off);
             if (r.d_occ) cudaFree(r.d_occ);
-            if (r.d_prefix_tables) cudaFree(r.d_prefix_tables);
         }
         cudaSetDevice(device);
         if (d_tree_parent) cudaFree(d_tree_parent);
         if (d_tree_lit) cudaFree(d_tree_lit);
-        for (int b = 0; b < 2; ++b)
+        if (d_get) cudaFree(d_get);
+        if (d_get_ptr) cudaFree((void*)d_get_ptr);
+        for (int b = 0; b < 2; ++b) {
             if (buf[b]) cudaFree(buf[b]);
+            if (sbuf[b]) cudaFree(sbuf[b]);
+        }
     }
 };
 
@@ -162,12 +215,88 @@ int check_device() {
     return NDP_OK;
 }
 
-int ensure_buf(ndp_frontier* f, int b, size_t slots) {
-    if (f->cap_slots[b] >= slots) return NDP_OK;
-    if (f->buf[b]) { CUDA_TRY(cudaFree(f->buf[b])); f->buf[b] = nullptr; f->cap_slots[b] = 0; }
-    size_t want = std::max(slots, (size_t)64);
-    CUDA_TRY(cudaMalloc(&f->buf[b], want * f->stride * sizeof(pclause)));
-    f->cap_slots[b] = want;
+// (re)allocate a DEAD arena buffer so that it holds `slots` slots of `slot_bytes`
+template <class T>
+int ensure_arena(T*& p, size_t& cap, size_t slots, size_t slot_bytes) {
+    if (cap >= slots) return NDP_OK;
+    if (p) { CUDA_TRY(cudaFree(p)); p = nullptr; cap = 0; }
+    const size_t want = std::max(slots, (size_t)64);
+    CUDA_TRY(cudaMalloc(&p, want * slot_bytes));
+    cap = want;
+    return NDP_OK;
+}
+
+// pack an int32 n x 3 clause array; returns false if a literal does not fit the 16-bit codes
+bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
+    for (size_t k = 0; k < n; ++k) {
+        for (int j = 0; j < 3; ++j) {
+            int l = c3[3 * k + j];
+            if (l > kMaxVar || l < -kMaxVar) return false;
+            int v = l < 0 ? -l : l;
+            if (v > max_var) max_var = v;
+        }
+        out[k] = pack_clause(c3[3 * k], c3[3 * k + 1], c3[3 * k + 2]);
+    }
+    return true;
+}
+
+// Root index of a BFS-born frontier on `device`: packed root + merged occurrence lists.
+int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
+    for (auto& r : f->root_indexes)
+        if (r.device == device) { *out = &r.ix; return NDP_OK; }
+    if (!f->has_root) return fail(NDP_E_INVALID, "this frontier has no root clause array (built by ndp_frontier_from_host)");
+    ndp_frontier::RootIndex r;
+    r.device = device;
+    const size_t n_root = f->root_c3.size() / 3;
+    const int V = f->max_var;
+    if (n_root >= (1u << 24)) return fail(NDP_E_UNSUPPORTED, "more than 2^24 root clauses");
+    std::vector<pclause> root(std::max(n_root, (size_t)1));
+    std::vector<unsigned> off((size_t)V + 2, 0), occ;
+    r.ix.n_zero3 = 0;
+    r.ix.first_zero3 = -1;
+    {
+        std::vector<std::vector<unsigned>> per_var((size_t)V + 1);
+        for (size_t c = 0; c < n_root; ++c) {
+            const int32_t* l = &f->root_c3[3 * c];
+            root[c] = pack_clause(l[0], l[1], l[2]);
+            if (!l[0] && !l[1] && !l[2]) { ++r.ix.n_zero3; if (r.ix.first_zero3 < 0) r.ix.first_zero3 = (int)c; }
+            for (int j = 0; j < 3; ++j) {
+                if (!l[j]) continue;
+                bool seen = false;
+                for (int i = 0; i < j; ++i) seen |= l[i] && std::abs(l[i]) == std::abs(l[j]);
+                if (seen) continue;   // one merged entry per (clause, variable)
+                unsigned n_pos = 0, n_neg = 0;
+                for (int i = 0; i < 3; ++i) {
+                    if (l[i] == std::abs(l[j])) ++n_pos;
+                    if (l[i] == -std::abs(l[j])) ++n_neg;
+                }
+                per_var[(size_t)std::abs(l[j])].push_back((unsigned)c | (n_pos << 24) | (n_neg << 26));
+            }
+        }
+        for (int v = 0; v <= V; ++v) {
+            off[v] = (unsigned)occ.size();
+            occ.insert(occ.end(), per_var[v].begin(), per_var[v].end());
+        }
+        off[(size_t)V + 1] = (unsigned)occ.size();
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(&r.d_root, root.size() * sizeof(pclause)));
+    CUDA_TRY(cudaMalloc(&r.d_occ_off, off.size() * 4));
+    CUDA_TRY(cudaMalloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
+    CUDA_TRY(cudaMemcpy(r.d_root, root.data(), root.size() * sizeof(pclause), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_occ_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    if (!occ.empty()) CUDA_TRY(cudaMemcpy(r.d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
+    f->h2d_bytes += root.size() * sizeof(pclause) + off.size() * 4 + occ.size() * 4;
+    r.ix.root = r.d_root;
+    r.ix.n_root = (int)n_root;
+    r.ix.occ_off = r.d_occ_off;
+    r.ix.occ = r.d_occ;
+    r.ix.bm_words = (int)((n_root + 31) / 32);
+    r.ix.table_words = (V + 1 + 15) / 16;
+    r.ix.slot_words = (3 * r.ix.bm_words + r.ix.table_words + 3) / 4 * 4;
+    if (r.ix.slot_words == 0) r.ix.slot_words = 4;
+    f->root_indexes.push_back(r);
+    *out = &f->root_indexes.back().ix;
     return NDP_OK;
 }
 
@@ -177,7 +306,8 @@ struct BfsLevelState {
     int32_t* node_tree[2] = {nullptr, nullptr};
     BfsChild* children = nullptr;
     int32_t *tree_parent = nullptr, *tree_lit = nullptr;
-    BfsLevelTotals* totals = nullptr;
+    BfsLevelTotals* totals = nullptr;        // device view of the host-mapped totals record
+    volatile BfsLevelTotals* h_totals = nullptr;
     size_t node_cap = 0, tree_cap = 0, tree_count = 0;
     int cur = 0;
 
@@ -190,7 +320,14 @@ struct BfsLevelState {
         return NDP_OK;
     }
     int reserve_nodes(size_t want) {
-        if (!totals) CUDA_TRY(cudaMalloc(&totals, sizeof(BfsLevelTotals)));
+        if (!totals) {
+            // the per-level totals are written straight into mapped pinned host memory: the host
+            // only has to wait for the stream, no copy is issued
+            void* h = nullptr;
+            CUDA_TRY(cudaHostAlloc(&h, sizeof(BfsLevelTotals), cudaHostAllocMapped));
+            h_totals = static_cast<volatile BfsLevelTotals*>(h);
+            CUDA_TRY(cudaHostGetDevicePointer((void**)&totals, h, 0));
+        }
         if (want <= node_cap) return NDP_OK;
         size_t cap = std::max(want, std::max(node_cap * 2, (size_t)4096));
         int rc;
@@ -226,22 +363,89 @@ struct BfsLevelState {
         if (children) cudaFree(children);
         if (tree_parent) cudaFree(tree_parent);
         if (tree_lit) cudaFree(tree_lit);
-        if (totals) cudaFree(totals);
+        if (h_totals) cudaFreeHost((void*)h_totals);
     }
 };
 
-// pack an int32 n x 3 clause array; returns false if a literal does not fit 16 bits
-bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
-    for (size_t k = 0; k < n; ++k) {
-        for (int j = 0; j < 3; ++j) {
-            int l = c3[3 * k + j];
-            if (l > kMaxVar || l < -kMaxVar) return false;
-            int v = l < 0 ? -l : l;
-            if (v > max_var) max_var = v;
-        }
-        out[k] = pack_clause(c3[3 * k], c3[3 * k + 1], c3[3 * k + 2]);
+int ensure_host_tree(ndp_frontier* f) {
+    if (f->host_tree_ready) return NDP_OK;
+    CUDA_TRY(cudaSetDevice(f->device));
+    f->tree_parent.resize(f->d_tree_count);
+    f->tree_lit.resize(f->d_tree_count);
+    CUDA_TRY(cudaMemcpy(f->tree_parent.data(), f->d_tree_parent, f->d_tree_count * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(f->tree_lit.data(), f->d_tree_lit, f->d_tree_count * 4, cudaMemcpyDeviceToHost));
+    f->d2h_bytes += f->d_tree_count * 8;
+    f->host_tree_ready = true;
+    return NDP_OK;
+}
+
+// choices of ONE element without bringing the whole tree home: walk it on the device
+int frontier_choices(ndp_frontier* f, size_t k, std::vector<int32_t>& out) {
+    const Entry& e = f->entries[k];
+    if (f->host_tree_ready || e.tree < 0) { f->choices_of(k, out); return NDP_OK; }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const int cap = std::max(f->max_var, 1) + 8;
+    DevBuf d_out, d_len;
+    CUDA_TRY(cudaMalloc(&d_out.p, (size_t)cap * 4));
+    CUDA_TRY(cudaMalloc(&d_len.p, 4));
+    tree_path_kernel<<<1, 1>>>(f->d_tree_parent, f->d_tree_lit, e.tree, d_out.as<int32_t>(), cap, d_len.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    int32_t len = 0;
+    CUDA_TRY(cudaMemcpy(&len, d_len.p, 4, cudaMemcpyDeviceToHost));
+    if (len > cap) {   // deeper than any variable count allows: fall back to the full tree
+        int rc = ensure_host_tree(f);
+        if (rc) return rc;
+        f->choices_of(k, out);
+        return NDP_OK;
     }
-    return true;
+    out.resize((size_t)len);
+    if (len) CUDA_TRY(cudaMemcpy(out.data(), d_out.p, (size_t)len * 4, cudaMemcpyDeviceToHost));
+    std::reverse(out.begin(), out.end());
+    return NDP_OK;
+}
+
+// Clause lists of a state frontier: element k -> out slot k (stride records each).
+int materialise(ndp_frontier* f, const std::vector<size_t>& which, pclause* d_out, size_t stride) {
+    const IndexRoot* ix = nullptr;
+    int rc = get_root_index(f, f->device, &ix);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(f->device));
+    std::vector<const unsigned*> ptrs(which.size());
+    for (size_t i = 0; i < which.size(); ++i) {
+        const Entry& e = f->entries[which[i]];
+        ptrs[i] = f->sbuf[e.buf] + (size_t)e.slot * ix->slot_words;
+    }
+    DevBuf d_ptr;
+    CUDA_TRY(cudaMalloc(&d_ptr.p, std::max(ptrs.size(), (size_t)1) * sizeof(unsigned*)));
+    CUDA_TRY(cudaMemcpy(d_ptr.p, ptrs.data(), ptrs.size() * sizeof(unsigned*), cudaMemcpyHostToDevice));
+    const int wpb = 4;
+    const int grid = (int)std::min<size_t>((which.size() + wpb - 1) / wpb, (size_t)148 * 16);
+    index_materialise_kernel<<<std::max(grid, 1), wpb * 32>>>(*ix, d_ptr.as<const unsigned*>(), (int)which.size(), d_out,
+                                                              stride, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return NDP_OK;
+}
+
+// Make buf[0] slot k hold entry k's clause list (what the scan DFS and bulk export read).
+int ensure_materialised(ndp_frontier* f) {
+    if (!f->states || f->materialised) return NDP_OK;
+    int n_max = 1;
+    for (const Entry& e : f->entries) n_max = std::max(n_max, e.n);
+    f->stride = (size_t)pad_up(n_max);
+    CUDA_TRY(cudaSetDevice(f->device));
+    int rc = ensure_arena(f->buf[0], f->cap_slots[0], std::max(f->entries.size(), (size_t)1), f->stride * sizeof(pclause));
+    if (rc) return rc;
+    std::vector<size_t> all(f->entries.size());
+    for (size_t k = 0; k < all.size(); ++k) all[k] = k;
+    if ((rc = materialise(f, all, f->buf[0], f->stride))) return rc;
+    f->materialised = true;
+    return NDP_OK;
+}
+
+const pclause* clause_slot(const ndp_frontier* f, size_t k) {
+    const Entry& e = f->entries[k];
+    return f->states ? f->buf[0] + k * f->stride : f->buf[e.buf] + (size_t)e.slot * f->stride;
 }
 
 }  // namespace
@@ -250,7 +454,7 @@ bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
 extern "C" {
 
 const char* ndp_last_error(void) { return g_err.c_str(); }
-const char* ndp_version(void) { return "ndp-b200 0.1 (NDP 5.6.7 hot path, sm_100a)"; }
+const char* ndp_version(void) { return "ndp-b200 0.2 (NDP 5.6.7 hot path, sm_100a; engines: scan, index)"; }
 
 int ndp_set_device(int device) {
     if (device < 0) return fail(NDP_E_INVALID, "negative device ordinal");
@@ -281,16 +485,20 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     if (n_clauses > (size_t)INT_MAX / 4) return fail(NDP_E_UNSUPPORTED, "too many clauses");
     int rc = check_device();
     if (rc) return rc;
+    const bool use_index = requested_engine() != NDP_ENGINE_SCAN;
 
+    const double t_start = now_ms();
+    double t_safe = 0, t_unsafe = 0;
+    size_t n_safe = 0, n_unsafe = 0;
     std::unique_ptr<ndp_frontier> f(new ndp_frontier);
     f->device = g_device;
     f->stride = std::max(n_clauses, (size_t)1);
     std::vector<pclause> packed(f->stride);
     if (!pack_host(clauses3, n_clauses, packed.data(), f->max_var))
         return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
-    if ((rc = ensure_buf(f.get(), 0, 64))) return rc;
-    CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
-    f->h2d_bytes += n_clauses * sizeof(pclause);
+    f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
+    f->has_root = true;
+    f->states = use_index;
 
     const int D = max_iterations, Q = max_queues;
     const bool ovr = override_max_iterations != 0;
@@ -304,19 +512,48 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     // can fire.
     BfsLevelState st;
     int status = NDP_OK;
-    {
-        BfsNode root{0, (int32_t)n_clauses, 0, 0};
-        host_setinfo(clauses3, n_clauses, root.kind, root.lit);
-        if ((status = st.reserve_nodes(1)) || (status = st.reserve_tree(1))) return status;
-        int32_t zero = 0, minus1 = -1;
+    const IndexRoot* ix = nullptr;
+    size_t slot_bytes = f->stride * sizeof(pclause);
+    BfsNode root{0, (int32_t)n_clauses, 0, 0};
+    host_setinfo(clauses3, n_clauses, root.kind, root.lit);
+    if ((status = st.reserve_nodes(1)) || (status = st.reserve_tree(1))) return status;
+    if (use_index) {
+        if ((rc = get_root_index(f.get(), f->device, &ix))) return rc;
+        slot_bytes = (size_t)ix->slot_words * 4;
+        if (8 * slot_bytes > 227 * 1024)
+            return fail(NDP_E_UNSUPPORTED, "root too large for the index engine's shared-memory state slots; use the scan engine");
+        CUDA_TRY(cudaFuncSetAttribute(bfs_index_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * slot_bytes)));
+        CUDA_TRY(cudaFuncSetAttribute(index_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * slot_bytes)));
+        if ((rc = ensure_arena(f->sbuf[0], f->scap_slots[0], 64, slot_bytes))) return rc;
+        // root state = the bitmaps of the empty assignment
+        DevBuf d_tab;
+        CUDA_TRY(cudaMalloc(&d_tab.p, std::max(ix->table_words, 1) * 4));
+        CUDA_TRY(cudaMemset(d_tab.p, 0, std::max(ix->table_words, 1) * 4));
+        index_states_kernel<<<1, 32, ix->slot_words * 4>>>(*ix, d_tab.as<unsigned>(), f->sbuf[0], 1, st.nodes[0]);
+        CUDA_TRY(cudaGetLastError());
+        BfsNode dev_root;
+        CUDA_TRY(cudaMemcpy(&dev_root, st.nodes[0], sizeof dev_root, cudaMemcpyDeviceToHost));
+        if (dev_root.n != root.n || dev_root.kind != root.kind || dev_root.lit != root.lit)
+            return fail(NDP_E_CUDA, "index root state disagrees with the host's choice()");
+        f->bfs_launches += 1;
+    } else {
+        if ((rc = ensure_arena(f->buf[0], f->cap_slots[0], 64, slot_bytes))) return rc;
+        CUDA_TRY(cudaMemcpy(f->buf[0], packed.data(), n_clauses * sizeof(pclause), cudaMemcpyHostToDevice));
+        f->h2d_bytes += n_clauses * sizeof(pclause);
         CUDA_TRY(cudaMemcpy(st.nodes[0], &root, sizeof root, cudaMemcpyHostToDevice));
+    }
+    {
+        int32_t zero = 0, minus1 = -1;
         CUDA_TRY(cudaMemcpy(st.node_tree[0], &zero, 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(st.tree_parent, &minus1, 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(st.tree_lit, &zero, 4, cudaMemcpyHostToDevice));
         st.tree_count = 1;
         f->h2d_bytes += sizeof root + 12;
     }
-    std::vector<cudaEvent_t> evs;          // one (start, stop) pair per level, summed at the end
+    cudaEvent_t ev_loop0, ev_loop1;        // device timeline of the whole level loop
+    CUDA_TRY(cudaEventCreate(&ev_loop0));
+    CUDA_TRY(cudaEventCreate(&ev_loop1));
+    CUDA_TRY(cudaEventRecord(ev_loop0, 0));
 
     std::vector<BfsNode> h_nodes;          // current level, only materialised on the host when needed
     std::vector<int32_t> h_node_tree;
@@ -324,15 +561,16 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     std::vector<Entry> final_entries;
     struct Pushed { int32_t parent_tree, lit; };
     std::vector<Pushed> host_tree_tail;    // tree entries created by the host walk of the stop level
-    bool done = false;
 
     // Level-synchronous restatement of the FIFO loop NDP:893-937: a FIFO
     // queue only ever holds the unexpanded rest of level L followed by the level-L+1 children
     // pushed so far, so walking one level in order with the running queue size `s` reproduces
     // every stop test at the exact pop it would fire.
-    while (!done) {
+    const double t_loop = now_ms();
+    for (;;) {
+        const double t_level = now_ms();
         if (m == 0) break;                                           // queue empty (NDP:893)
-        bool stop_at_top = (Q > 0 && m >= (size_t)Q) || (D == -1 && !ovr);   // NDP:894-897 before the first pop
+        const bool stop_at_top = (Q > 0 && m >= (size_t)Q) || (D == -1 && !ovr);   // NDP:894-897 before the first pop
         size_t need = m;
         if (!stop_at_top && Q <= 0) {                                // -d budget known in advance
             long long R = (long long)D - it;
@@ -343,47 +581,52 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         const bool safe = !stop_at_top && (Q > 0 ? 2 * m < (size_t)Q : (it + (long long)m < (long long)D));
         if (stop_at_top) {
             if ((status = st.download_level(m, h_nodes, h_node_tree, f->d2h_bytes))) break;
-            for (size_t j = 0; j < m; ++j) final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j]});
+            for (size_t j = 0; j < m; ++j)
+                final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j], h_nodes[j].kind, h_nodes[j].lit});
             break;
         }
         {
             // grow the (dead) target buffer geometrically, but never past what the stop rule
             // allows a level to reach: width <= Q under -q, <= D+1 under -d
             size_t want = 2 * need;
-            if (f->cap_slots[cur_buf ^ 1] < want) {
+            size_t& cap = use_index ? f->scap_slots[cur_buf ^ 1] : f->cap_slots[cur_buf ^ 1];
+            if (cap < want) {
                 size_t bound = SIZE_MAX;
                 if (Q > 0) bound = 2 * (size_t)Q;
                 else if (D > 0) bound = 2 * ((size_t)D + 1);
-                want = std::min(std::max(want, f->cap_slots[cur_buf ^ 1] * 2), std::max(bound, want));
+                want = std::min(std::max(want, cap * 2), std::max(bound, want));
             }
-            status = ensure_buf(f.get(), cur_buf ^ 1, want);
+            auto grow = [&](size_t slots) {
+                return use_index ? ensure_arena(f->sbuf[cur_buf ^ 1], f->scap_slots[cur_buf ^ 1], slots, slot_bytes)
+                                 : ensure_arena(f->buf[cur_buf ^ 1], f->cap_slots[cur_buf ^ 1], slots, slot_bytes);
+            };
+            status = grow(want);
             if (status == NDP_E_NOMEM && want > 2 * need) {   // head-room did not fit: take the exact size
                 cudaGetLastError();
-                status = ensure_buf(f.get(), cur_buf ^ 1, 2 * need);
+                status = grow(2 * need);
             }
             if (status) break;
         }
         if ((status = st.reserve_nodes(2 * need)) || (status = st.reserve_tree(st.tree_count + 2 * need))) break;
         const int warps_per_block = 8;
         int grid = (int)std::min<size_t>((need + warps_per_block - 1) / warps_per_block, (size_t)148 * 16);
-        cudaEvent_t ea, eb;
-        cudaEventCreate(&ea);
-        cudaEventCreate(&eb);
-        evs.push_back(ea);
-        evs.push_back(eb);
-        cudaEventRecord(ea, 0);
-        bfs_expand_kernel<<<grid, warps_per_block * 32>>>(f->buf[cur_buf], f->buf[cur_buf ^ 1], f->stride,
-                                                          st.nodes[st.cur], (int)need, st.children);
+        if (use_index)
+            bfs_index_expand_kernel<<<grid, warps_per_block * 32, (size_t)warps_per_block * ix->slot_words * 4>>>(
+                *ix, f->sbuf[cur_buf], f->sbuf[cur_buf ^ 1], st.nodes[st.cur], (int)need, st.children);
+        else
+            bfs_expand_kernel<<<grid, warps_per_block * 32>>>(f->buf[cur_buf], f->buf[cur_buf ^ 1], f->stride,
+                                                              st.nodes[st.cur], (int)need, st.children);
         bfs_compact_kernel<<<1, 1024>>>(st.nodes[st.cur], st.node_tree[st.cur], st.children, (int)need,
                                         st.nodes[st.cur ^ 1], st.node_tree[st.cur ^ 1], st.tree_parent, st.tree_lit,
-                                        (int)st.tree_count, st.totals);
-        cudaEventRecord(eb, 0);
+                                        (int)st.tree_count, Q, st.totals);
         f->bfs_launches += 2;
-        BfsLevelTotals tot;
-        cudaError_t ce = cudaMemcpy(&tot, st.totals, sizeof tot, cudaMemcpyDeviceToHost);
+        cudaError_t ce = cudaStreamSynchronize(0);
         if (ce != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS level: ") + cudaGetErrorString(ce)); break; }
+        BfsLevelTotals tot;
+        memcpy(&tot, (const void*)st.h_totals, sizeof tot);
         f->d2h_bytes += sizeof tot;
-        if (safe) {
+        // -q: the device checked the "queue size >= Q before a pop" test at every node of the level
+        if (safe || (Q > 0 && !tot.stop_q)) {
             // every node of the level is expanded; only the totals matter
             it += (long long)tot.expanded;
             task_count += (long long)tot.m_next;
@@ -392,6 +635,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
             st.cur ^= 1;
             cur_buf ^= 1;
             m = tot.m_next;
+            t_safe += now_ms() - t_level;
+            ++n_safe;
             continue;
         }
         // a stop test can fire here: walk the level on the host with the exact rules
@@ -416,7 +661,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 if (c.n < 0) continue;
                 int32_t tree = (int32_t)(st.tree_count + host_tree_tail.size());
                 host_tree_tail.push_back(Pushed{h_node_tree[j], b == 0 ? var : -var});
-                next_entries.push_back(Entry{cur_buf ^ 1, (uint32_t)(2 * j + b), c.n, tree});
+                next_entries.push_back(Entry{cur_buf ^ 1, (uint32_t)(2 * j + b), c.n, tree, c.kind, c.lit});
                 ++task_count;
                 ++s;
             }
@@ -425,9 +670,9 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         }
         if (stopped || E < m) {
             // frontier = unexpanded rest of the current level, then the children pushed so far
-            for (size_t j = E; j < m; ++j) final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j]});
+            for (size_t j = E; j < m; ++j)
+                final_entries.push_back(Entry{cur_buf, h_nodes[j].slot, h_nodes[j].n, h_node_tree[j], h_nodes[j].kind, h_nodes[j].lit});
             final_entries.insert(final_entries.end(), next_entries.begin(), next_entries.end());
-            done = true;
             break;
         }
         // no stop fired: the device-side compaction of this level is exactly what the walk produced
@@ -436,40 +681,43 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         st.cur ^= 1;
         cur_buf ^= 1;
         m = tot.m_next;
+        t_unsafe += now_ms() - t_level;
+        ++n_unsafe;
     }
+    cudaEventRecord(ev_loop1, 0);
     cudaDeviceSynchronize();
-    for (size_t e = 0; e + 1 < evs.size(); e += 2) {
+    const double t_loop_end = now_ms();
+    {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, evs[e], evs[e + 1]) == cudaSuccess) f->bfs_kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, ev_loop0, ev_loop1) == cudaSuccess) f->bfs_kernel_ms = ms;
+        cudaEventDestroy(ev_loop0);
+        cudaEventDestroy(ev_loop1);
     }
-    for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (status) return status;
 
-    // bring the choice tree home (parent pointers + literals), then the stop level's tail
-    f->tree_parent.resize(st.tree_count);
-    f->tree_lit.resize(st.tree_count);
-    CUDA_TRY(cudaMemcpy(f->tree_parent.data(), st.tree_parent, st.tree_count * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(f->tree_lit.data(), st.tree_lit, st.tree_count * 4, cudaMemcpyDeviceToHost));
-    f->d2h_bytes += st.tree_count * 8;
-    for (const Pushed& p : host_tree_tail) { f->tree_parent.push_back(p.parent_tree); f->tree_lit.push_back(p.lit); }
+    // The choice tree stays on the device (completed with the stop level's tail); the host copy is
+    // fetched lazily, only if choices of many elements are asked for (ndp_frontier_get / -s).
     f->entries.swap(final_entries);
-    // the index engine derives every subproblem from the root + its choices: keep the root and
-    // leave the tree on the device (completed with the stop level's tail)
-    f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
-    f->has_root = true;
     if (!host_tree_tail.empty()) {
-        if ((status = st.reserve_tree(f->tree_parent.size()))) return status;
-        CUDA_TRY(cudaMemcpy(st.tree_parent + st.tree_count, f->tree_parent.data() + st.tree_count,
-                            host_tree_tail.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(st.tree_lit + st.tree_count, f->tree_lit.data() + st.tree_count,
-                            host_tree_tail.size() * 4, cudaMemcpyHostToDevice));
+        if ((status = st.reserve_tree(st.tree_count + host_tree_tail.size()))) return status;
+        std::vector<int32_t> tp(host_tree_tail.size()), tl(host_tree_tail.size());
+        for (size_t i = 0; i < host_tree_tail.size(); ++i) { tp[i] = host_tree_tail[i].parent_tree; tl[i] = host_tree_tail[i].lit; }
+        CUDA_TRY(cudaMemcpy(st.tree_parent + st.tree_count, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(st.tree_lit + st.tree_count, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice));
         f->h2d_bytes += host_tree_tail.size() * 8;
     }
+    f->d_tree_count = st.tree_count + host_tree_tail.size();
+    f->host_tree_ready = false;
     f->d_tree_parent = st.tree_parent;
     f->d_tree_lit = st.tree_lit;
     st.tree_parent = nullptr;   // ownership moves to the frontier
     st.tree_lit = nullptr;
 
+    if (tracing())
+        fprintf(stderr, "[ndp_bfs] setup %.2f ms | loop %.2f ms (safe levels %zu: %.2f ms, walked levels %zu: %.2f ms) | "
+                        "finish %.2f ms | kernels %.2f ms\n",
+                t_loop - t_start, t_loop_end - t_loop, n_safe, t_safe, n_unsafe, t_unsafe, now_ms() - t_loop_end,
+                f->bfs_kernel_ms);
     if (iterations_out) *iterations_out = (int)it;
     if (task_count_out) *task_count_out = (int)task_count;
     if (initial_queue_size && *initial_queue_size == 0) *initial_queue_size = f->entries.size();  // NDP:939-941
@@ -497,7 +745,11 @@ size_t ndp_frontier_size(const ndp_frontier* f) { return f ? f->entries.size() :
 int ndp_frontier_dims(const ndp_frontier* f, size_t k, size_t* n_clauses, size_t* n_choices) {
     if (!f || k >= f->entries.size()) return fail(NDP_E_INVALID, "frontier index out of range");
     if (n_clauses) *n_clauses = (size_t)f->entries[k].n;
-    if (n_choices) *n_choices = f->nchoices_of(k);
+    if (n_choices) {
+        int rc = ensure_host_tree(const_cast<ndp_frontier*>(f));
+        if (rc) return rc;
+        *n_choices = f->nchoices_of(k);
+    }
     return NDP_OK;
 }
 
@@ -507,14 +759,23 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
     const Entry& e = f->entries[k];
     if (clauses3 || n_clauses) {
         CUDA_TRY(cudaSetDevice(f->device));
+        const pclause* src;
+        if (f->states && !f->materialised) {
+            // one element: filter the root by this node's assignment into a scratch slot
+            const size_t cap = (size_t)pad_up((int)(f->root_c3.size() / 3) + 1);
+            if (!f->d_get) CUDA_TRY(cudaMalloc(&f->d_get, cap * sizeof(pclause)));
+            int rc = materialise(f, std::vector<size_t>{k}, f->d_get, cap);
+            if (rc) return rc;
+            src = f->d_get;
+        } else {
+            src = clause_slot(f, k);
+        }
         f->get_packed.resize((size_t)std::max(e.n, 1));
-        CUDA_TRY(cudaMemcpy(f->get_packed.data(), f->buf[e.buf] + (size_t)e.slot * f->stride,
-                            (size_t)e.n * sizeof(pclause), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(f->get_packed.data(), src, (size_t)e.n * sizeof(pclause), cudaMemcpyDeviceToHost));
         f->get_clauses.resize((size_t)e.n * 3 + 1);
         for (int32_t c = 0; c < e.n; ++c) {
-            const pclause p = f->get_packed[c];
             int l0, l1, l2;
-            unpack_clause(p, l0, l1, l2);
+            unpack_clause(f->get_packed[c], l0, l1, l2);
             f->get_clauses[3 * c] = l0;
             f->get_clauses[3 * c + 1] = l1;
             f->get_clauses[3 * c + 2] = l2;
@@ -523,6 +784,8 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
         if (n_clauses) *n_clauses = (size_t)e.n;
     }
     if (choices || n_choices) {
+        int rc = ensure_host_tree(f);
+        if (rc) return rc;
         f->choices_of(k, f->get_choices);
         if (f->get_choices.empty()) f->get_choices.reserve(1);
         if (choices) *choices = f->get_choices.data();
@@ -548,7 +811,7 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
     }
     if (stride > (size_t)INT_MAX / 4) return fail(NDP_E_UNSUPPORTED, "clause set too large");
     f->stride = stride;
-    if ((rc = ensure_buf(f.get(), 0, std::max(count, (size_t)1)))) return rc;
+    if ((rc = ensure_arena(f->buf[0], f->cap_slots[0], std::max(count, (size_t)1), stride * sizeof(pclause)))) return rc;
     // stage in bounded chunks so a multi-GB resume does not double its footprint on the host
     const size_t chunk_slots = std::max<size_t>(1, ((size_t)64 << 20) / (stride * sizeof(pclause)));
     std::vector<pclause> stage(chunk_slots * stride);
@@ -558,7 +821,7 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
             size_t n = clause_offsets[k + 1] - clause_offsets[k];
             if (!pack_host(clauses3 + 3 * clause_offsets[k], n, stage.data() + (k - k0) * stride, f->max_var))
                 return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
-            f->entries.push_back(Entry{0, (uint32_t)k, (int32_t)n, -1});
+            f->entries.push_back(Entry{0, (uint32_t)k, (int32_t)n, -1, 0, 0});
         }
         CUDA_TRY(cudaMemcpy(f->buf[0] + k0 * stride, stage.data(), (k1 - k0) * stride * sizeof(pclause),
                             cudaMemcpyHostToDevice));
@@ -630,6 +893,8 @@ int plan_dfs(int device, int n_max, int max_var, DfsLaunchPlan& plan) {
 int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_frontier::Replica** out) {
     for (auto& r : f->replicas)
         if (r.device == device && r.first == first && r.stride == stride) { *out = &r; return NDP_OK; }
+    int rc = ensure_materialised(f);   // a state frontier searched by the scan engine needs clause lists
+    if (rc) return rc;
     ndp_frontier::Replica r;
     r.device = device;
     r.first = first;
@@ -643,18 +908,17 @@ int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_
         // private copy of this shard's slots on the other GPU, one peer copy per slot
         CUDA_TRY(cudaMalloc(&r.shard_buf, r.n_local * f->stride * sizeof(pclause)));
         for (size_t q = 0; q < r.n_local; ++q) {
-            const Entry& e = f->entries[first + q * stride];
-            CUDA_TRY(cudaMemcpyPeerAsync(r.shard_buf + q * f->stride, device,
-                                         f->buf[e.buf] + (size_t)e.slot * f->stride, f->device,
-                                         (size_t)e.n * sizeof(pclause), 0));
+            const size_t k = first + q * stride;
+            CUDA_TRY(cudaMemcpyPeerAsync(r.shard_buf + q * f->stride, device, clause_slot(f, k), f->device,
+                                         (size_t)f->entries[k].n * sizeof(pclause), 0));
         }
         CUDA_TRY(cudaStreamSynchronize(0));
     }
     for (size_t q = 0; q < r.n_local; ++q) {
-        const Entry& e = f->entries[first + q * stride];
-        h_base[q] = r.shard_buf ? r.shard_buf + q * f->stride : f->buf[e.buf] + (size_t)e.slot * f->stride;
-        h_n[q] = e.n;
-        r.n_max = std::max(r.n_max, e.n);
+        const size_t k = first + q * stride;
+        h_base[q] = r.shard_buf ? r.shard_buf + q * f->stride : clause_slot(f, k);
+        h_n[q] = f->entries[k].n;
+        r.n_max = std::max(r.n_max, f->entries[k].n);
     }
     CUDA_TRY(cudaMalloc((void**)&r.d_base, h_base.size() * sizeof(pclause*)));
     CUDA_TRY(cudaMalloc(&r.d_n, h_n.size() * sizeof(int32_t)));
@@ -665,23 +929,10 @@ int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_
     return NDP_OK;
 }
 
-struct DevBuf {  // tiny RAII for the per-call device outputs
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    template <class T> T* as() { return static_cast<T*>(p); }
-};
-
-// ---- index engine ---------------------------------------------------------------------------
-
+// ---- index DFS ------------------------------------------------------------------------------
 bool engine_uses_index(const ndp_frontier* f) {
-    int e = g_engine;
-    if (e == NDP_ENGINE_AUTO) {
-        const char* s = getenv("NDP_ENGINE");
-        if (s && !strcmp(s, "scan")) e = NDP_ENGINE_SCAN;
-        else if (s && !strcmp(s, "index")) e = NDP_ENGINE_INDEX;
-    }
     if (!f->has_root) return false;   // explicit clause sets (resume): no common root to index
-    return e != NDP_ENGINE_SCAN;
+    return requested_engine() != NDP_ENGINE_SCAN;
 }
 
 struct IndexLaunchPlan {
@@ -689,18 +940,16 @@ struct IndexLaunchPlan {
     IndexParams p;
 };
 
-int plan_index(int device, int n_root, int max_var, IndexLaunchPlan& plan) {
+int plan_index(int device, const IndexRoot& ix, int max_var, IndexLaunchPlan& plan) {
     int sms = 0, smem_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     IndexParams& p = plan.p;
-    p.bm_words = (n_root + 31) / 32;
-    p.table_words = (max_var + 1 + 15) / 16;
+    p.ix = ix;
     p.trail_cap = std::max(max_var, 1);
     p.pend_words = (p.trail_cap + 31) / 32;
-    size_t off = align16((size_t)3 * p.bm_words * 4);
-    p.off_table = (int)off; off += align16((size_t)p.table_words * 4);
+    size_t off = align16((size_t)ix.slot_words * 4);
     p.off_pend = (int)off;  off += align16((size_t)p.pend_words * 4);
     p.warp_bytes = (int)std::max(off, (size_t)16);
     if ((size_t)p.warp_bytes > (size_t)smem_optin)
@@ -723,7 +972,11 @@ int plan_index(int device, int n_root, int max_var, IndexLaunchPlan& plan) {
     return NDP_OK;
 }
 
-int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_frontier::IndexReplica** out) {
+int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride, const IndexRoot** ix_out,
+                        ndp_frontier::IndexReplica** out) {
+    int rc = get_root_index(f, device, ix_out);
+    if (rc) return rc;
+    const IndexRoot& ix = **ix_out;
     for (auto& r : f->index_replicas)
         if (r.device == device && r.first == first && r.stride == stride) { *out = &r; return NDP_OK; }
     ndp_frontier::IndexReplica r;
@@ -732,59 +985,46 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
     r.stride = stride;
     const size_t total = f->entries.size();
     r.n_local = first < total ? (total - first + stride - 1) / stride : 0;
-    const size_t n_root = f->root_c3.size() / 3;
-    const int V = f->max_var;
-    // root records + merged occurrence lists (c | n_pos << 24 | n_neg << 26), built on the host once
-    std::vector<pclause> root(std::max(n_root, (size_t)1));
-    std::vector<unsigned> off((size_t)V + 2, 0), occ;
-    if (n_root >= (1u << 24)) return fail(NDP_E_UNSUPPORTED, "more than 2^24 root clauses");
-    {
-        std::vector<std::vector<unsigned>> per_var((size_t)V + 1);
-        for (size_t c = 0; c < n_root; ++c) {
-            const int32_t* l = &f->root_c3[3 * c];
-            root[c] = pack_clause(l[0], l[1], l[2]);
-            if (!l[0] && !l[1] && !l[2]) { ++r.n_zero3; if (r.first_zero3 < 0) r.first_zero3 = (int)c; }
-            for (int j = 0; j < 3; ++j) {
-                if (!l[j]) continue;
-                bool seen = false;
-                for (int i = 0; i < j; ++i) seen |= l[i] && std::abs(l[i]) == std::abs(l[j]);
-                if (seen) continue;
-                unsigned n_pos = 0, n_neg = 0;
-                for (int i = 0; i < 3; ++i) {
-                    if (l[i] == std::abs(l[j])) ++n_pos;
-                    if (l[i] == -std::abs(l[j])) ++n_neg;
-                }
-                per_var[(size_t)std::abs(l[j])].push_back((unsigned)c | (n_pos << 24) | (n_neg << 26));
-            }
-        }
-        for (int v = 0; v <= V; ++v) {
-            off[v] = (unsigned)occ.size();
-            occ.insert(occ.end(), per_var[v].begin(), per_var[v].end());
-        }
-        off[(size_t)V + 1] = (unsigned)occ.size();
-    }
-    r.table_words = (V + 1 + 15) / 16;
+    const size_t nl1 = std::max(r.n_local, (size_t)1);
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMalloc(&r.d_root, root.size() * sizeof(pclause)));
-    CUDA_TRY(cudaMalloc(&r.d_occ_off, off.size() * 4));
-    CUDA_TRY(cudaMalloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
-    CUDA_TRY(cudaMemcpy(r.d_root, root.data(), root.size() * sizeof(pclause), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(r.d_occ_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-    if (!occ.empty()) CUDA_TRY(cudaMemcpy(r.d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
-    f->h2d_bytes += root.size() * sizeof(pclause) + off.size() * 4 + occ.size() * 4;
-    // each subproblem's choices as a 2-bit assignment table, derived on the device from the tree
-    const size_t tbytes = std::max(r.n_local, (size_t)1) * r.table_words * 4;
-    CUDA_TRY(cudaMalloc(&r.d_prefix_tables, tbytes));
-    CUDA_TRY(cudaMemset(r.d_prefix_tables, 0, tbytes));
-    if (r.n_local) {
+    CUDA_TRY(cudaMalloc((void**)&r.d_slot_ptr, nl1 * sizeof(unsigned*)));
+    CUDA_TRY(cudaMalloc(&r.d_meta, nl1 * sizeof(BfsNode)));
+    std::vector<const unsigned*> h_ptr(nl1, nullptr);
+    std::vector<BfsNode> h_meta(nl1);
+    if (f->states) {
+        // the BFS already produced state slots: use them in place (home device) or copy the shard over
+        if (device != f->device && r.n_local) {
+            CUDA_TRY(cudaMalloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
+            for (size_t q = 0; q < r.n_local; ++q) {
+                const Entry& e = f->entries[first + q * stride];
+                CUDA_TRY(cudaMemcpyPeerAsync(r.own_slots + q * ix.slot_words, device,
+                                             f->sbuf[e.buf] + (size_t)e.slot * ix.slot_words, f->device,
+                                             (size_t)ix.slot_words * 4, 0));
+            }
+            CUDA_TRY(cudaStreamSynchronize(0));
+        }
+        for (size_t q = 0; q < r.n_local; ++q) {
+            const Entry& e = f->entries[first + q * stride];
+            h_ptr[q] = r.own_slots ? r.own_slots + q * ix.slot_words : f->sbuf[e.buf] + (size_t)e.slot * ix.slot_words;
+            h_meta[q] = BfsNode{(uint32_t)q, e.n, e.kind, e.lit};
+        }
+        CUDA_TRY(cudaMemcpy(r.d_meta, h_meta.data(), nl1 * sizeof(BfsNode), cudaMemcpyHostToDevice));
+    } else if (r.n_local) {
+        // clause-slot frontier with a root: each subproblem's choices -> assignment table (walking the
+        // tree on the device) -> state slot
+        DevBuf d_tables, d_entry, d_tp, d_tl;
+        const size_t tbytes = r.n_local * (size_t)ix.table_words * 4;
+        CUDA_TRY(cudaMalloc(&d_tables.p, std::max(tbytes, (size_t)4)));
+        CUDA_TRY(cudaMemset(d_tables.p, 0, std::max(tbytes, (size_t)4)));
         std::vector<int32_t> h_entry_tree(total);
         for (size_t k = 0; k < total; ++k) h_entry_tree[k] = f->entries[k].tree;
-        DevBuf d_entry, d_tp, d_tl;
         CUDA_TRY(cudaMalloc(&d_entry.p, total * 4));
         CUDA_TRY(cudaMemcpy(d_entry.p, h_entry_tree.data(), total * 4, cudaMemcpyHostToDevice));
         f->h2d_bytes += total * 4;
         const int32_t *tp = f->d_tree_parent, *tl = f->d_tree_lit;
         if (device != f->device || !tp) {   // another GPU: ship the tree from the host copy
+            if ((rc = ensure_host_tree(f))) return rc;
+            CUDA_TRY(cudaSetDevice(device));
             const size_t tn = f->tree_parent.size();
             CUDA_TRY(cudaMalloc(&d_tp.p, tn * 4));
             CUDA_TRY(cudaMalloc(&d_tl.p, tn * 4));
@@ -797,16 +1037,25 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
         const int threads = 128;
         const int blocks = (int)std::min<size_t>((r.n_local + threads - 1) / threads, 4096);
         prefix_table_kernel<<<blocks, threads>>>(d_entry.as<int32_t>(), tp, tl, first, stride, r.n_local,
-                                                 r.table_words, r.d_prefix_tables);
+                                                 ix.table_words, d_tables.as<unsigned>());
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMalloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
+        const int wpb = 4;
+        const int grid = (int)std::min<size_t>((r.n_local + wpb - 1) / wpb, (size_t)148 * 16);
+        index_states_kernel<<<grid, wpb * 32, wpb * ix.slot_words * 4>>>(ix, d_tables.as<unsigned>(), r.own_slots,
+                                                                        (int)r.n_local, r.d_meta);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
+        for (size_t q = 0; q < r.n_local; ++q) h_ptr[q] = r.own_slots + q * ix.slot_words;
     }
+    CUDA_TRY(cudaMemcpy((void*)r.d_slot_ptr, h_ptr.data(), nl1 * sizeof(unsigned*), cudaMemcpyHostToDevice));
+    f->h2d_bytes += nl1 * (sizeof(unsigned*) + sizeof(BfsNode));
     f->index_replicas.push_back(r);
     *out = &f->index_replicas.back();
     return NDP_OK;
 }
 
-// One shard on one device.  `best_dev`/`peers`: early-exit words (this device's + peers').
+// One shard on one device.  `shared_best`/`peer_best`: early-exit words (this device's + peers').
 int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int early_exit,
                   unsigned long long* shared_best, unsigned long long* const* peer_best, int n_peers,
                   unsigned long long best_init, uint8_t* verdict, size_t* winner, std::vector<int32_t>* model,
@@ -815,7 +1064,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     int rc;
     ndp_frontier::Replica* rep = nullptr;
     ndp_frontier::IndexReplica* irep = nullptr;
-    if (use_index) rc = build_index_replica(f, device, first, stride, &irep);
+    const IndexRoot* ix = nullptr;
+    if (use_index) rc = build_index_replica(f, device, first, stride, &ix, &irep);
     else rc = build_replica(f, device, first, stride, &rep);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
@@ -828,7 +1078,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     IndexLaunchPlan iplan;
     int n_warps, model_stride;
     if (use_index) {
-        if ((rc = plan_index(device, (int)(f->root_c3.size() / 3), f->max_var, iplan))) return rc;
+        if ((rc = plan_index(device, *ix, f->max_var, iplan))) return rc;
         n_warps = iplan.grid * iplan.warps_per_cta;
         model_stride = iplan.p.trail_cap;
     } else {
@@ -864,13 +1114,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(cudaEventCreate(&ev1));
     if (use_index) {
         IndexParams& p = iplan.p;
-        p.root = irep->d_root;
-        p.n_root = (int)(f->root_c3.size() / 3);
-        p.occ_off = irep->d_occ_off;
-        p.occ = irep->d_occ;
-        p.prefix_tables = irep->d_prefix_tables;
-        p.n_zero3 = irep->n_zero3;
-        p.first_zero3 = irep->first_zero3;
+        p.slot_ptr = irep->d_slot_ptr;
+        p.meta = irep->d_meta;
         p.first = first; p.stride = stride; p.n_local = nl;
         p.next = b_next.as<unsigned int>();
         p.best = d_best;
@@ -953,7 +1198,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         model->clear();
         for (int w = 0; w < n_warps; ++w)
             if (h_msub[w] == (unsigned long long)win) {
-                f->choices_of(win, *model);                       // choices_k ++ dfs choices (NDP:1430-1431)
+                if ((rc = frontier_choices(f, win, *model))) return rc;   // choices_k ++ dfs choices (NDP:1430-1431)
                 std::vector<int32_t> tail((size_t)h_mlen[w]);
                 CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * model_stride,
                                     tail.size() * 4, cudaMemcpyDeviceToHost));
@@ -1038,9 +1283,16 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         CUDA_TRY(cudaMemcpy(best[i], &none, 8, cudaMemcpyHostToDevice));
     }
     // build replicas serially (peer copies from the home device), then search concurrently
+    const bool use_index = engine_uses_index(f);
     for (int i = 0; i < n_gpus; ++i) {
-        ndp_frontier::Replica* rep = nullptr;
-        if ((rc = build_replica(f, devs[i], (size_t)i, (size_t)n_gpus, &rep))) return rc;
+        if (use_index) {
+            const IndexRoot* ix = nullptr;
+            ndp_frontier::IndexReplica* rep = nullptr;
+            if ((rc = build_index_replica(f, devs[i], (size_t)i, (size_t)n_gpus, &ix, &rep))) return rc;
+        } else {
+            ndp_frontier::Replica* rep = nullptr;
+            if ((rc = build_replica(f, devs[i], (size_t)i, (size_t)n_gpus, &rep))) return rc;
+        }
     }
     std::vector<int> rcs(n_gpus, 0);
     std::vector<std::string> errs(n_gpus);

@@ -1,57 +1,43 @@
-// ndp_index.cuh -- the occurrence-index DFS engine.
+// ndp_index.cuh -- the occurrence-index engine (BFS levels and DFS).
 //
-// Same search as dfs_kernel (ndp_kernels.cuh) -- the reference's Satisfy_iterative node for node
-// (NDP-5_6_7.cpp:784-878), same choices in the same order, same node and clause-evaluation
-// counts -- but a node no longer scans its clause set to find the ~dozen clauses that mention the
-// assigned variable.  All subproblems of a BFS frontier are the ROOT clause array filtered by an
-// assignment (SURVEY.md §8a equivalences), so one read-only index over the root serves them all:
+// Same search as the scan engine (ndp_kernels.cuh) -- the reference's Satisfy_iterative_BFS /
+// Satisfy_iterative node for node (NDP-5_6_7.cpp:881-944, 784-878), same choices in the same
+// order, same node and clause-evaluation counts -- but a node no longer scans its clause set to
+// find the ~dozen clauses that mention the assigned variable.  Every node of a run is the ROOT
+// clause array filtered by an assignment (SURVEY.md §8a equivalences), so one read-only index
+// over the root serves them all:
 //
 //   root[c]      the packed root clause (ndp_clause.cuh record; zc = zeros it was parsed with)
 //   occ[v]       clauses that mention variable v, merged per clause: c | n_pos << 24 | n_neg << 26
 //                (n_pos / n_neg = how many of the clause's literals are +v / -v, so duplicate
 //                literals and tautologies need no special case)
 //
-// and a warp's whole search state is three bitmaps over root clause ids plus the assignment:
+// and a node's whole state ("state slot") is three bitmaps over root clause ids plus the assignment:
 //
 //   B[k] (k = 0,1,2)  clause is live and currently has exactly k zero literals
 //   table             2 bits per variable (0 unassigned, 1 true, 2 false)
-//   trail, pend       choices in decision order (global memory) and the pending-sibling bits
 //
 // choice() (NDP:753-781) becomes find-first-set: the first live two-zero clause is the lowest set
 // bit of B[2], the first one-zero clause that of B[1], A[0] that of B[0].  Resolution
-// (NDP:654-697) becomes: walk occ[v]; a clause holding the true literal leaves its bitmap
-// (satisfied, dropped); one holding only false literals moves from B[k] to B[k + n_false], and
-// reaching three zeros is the conflict.  A popped sibling is re-derived from the table with one
-// pass over the root (no stack of clause sets).
+// (NDP:654-697 / 700-750) becomes: walk occ[v]; a clause holding the true literal leaves its
+// bitmap (satisfied, dropped); one holding only false literals moves from B[k] to B[k + n_false],
+// and reaching three zeros is the conflict.  The materialised clause list of a node (needed only
+// for -s JSON, ndp_frontier_get and the scan engine) is the root filtered by its table.
 #pragma once
 #include "ndp_clause.cuh"
+#include "ndp_kernels.cuh"
 
 namespace ndp {
 
-struct IndexParams {
+struct IndexRoot {
     const pclause* root;              // [n_root]
     int n_root;
     const unsigned* occ_off;          // [max_var + 2]
     const unsigned* occ;              // merged occurrence entries
-    const unsigned* prefix_tables;    // [n_local][table_words]: assignment of each subproblem's choices
-    int table_words, bm_words, pend_words, trail_cap;
+    int bm_words, table_words;
+    int slot_words;                   // 3 * bm_words + table_words, rounded up to a multiple of 4
     int n_zero3;                      // root clauses that are {0,0,0} (never leave, always conflict)
     int first_zero3;                  // lowest such index, or -1
-    unsigned long long first, stride, n_local;
-    unsigned int* next;
-    unsigned long long* best;
-    unsigned long long* peer_best[8];
-    int n_peers;
-    int early_exit;
-    uint8_t* verdict;
-    unsigned long long* nodes;
-    unsigned long long* evals;
-    unsigned int* rebuilds;
-    unsigned long long* model_sub;    // [n_warps]
-    int32_t* model_len;               // [n_warps]
-    short* trails;                    // [n_warps][trail_cap] working trail of each warp
-    int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
-    int warp_bytes, off_table, off_pend;   // shared-memory layout of one warp: B[3][bm_words], table, pend
 };
 
 // lowest set bit of a bitmap of `words` words, or -1
@@ -71,14 +57,14 @@ __device__ __forceinline__ int bitmap_first(const unsigned* B, int words, unsign
 
 // Derive the three bitmaps from the assignment table with one pass over the root.
 // Returns the number of live clauses (all-zero root clauses included: they are part of |A|).
-__device__ __noinline__ int index_rebuild(const IndexParams& p, unsigned* B, const unsigned* table, unsigned lane) {
+__device__ __noinline__ int index_rebuild(const IndexRoot& ix, unsigned* B, const unsigned* table, unsigned lane) {
     int n_live = 0;
-    for (int base = 0; base < p.bm_words * 32; base += 32) {
+    for (int base = 0; base < ix.bm_words * 32; base += 32) {
         const int c = base + (int)lane;
         bool live = false;
         unsigned zc = 0;
-        if (c < p.n_root) {
-            const pclause cl = __ldg(&p.root[c]);
+        if (c < ix.n_root) {
+            const pclause cl = __ldg(&ix.root[c]);
             const unsigned f[3] = {cl.x & 0xffffu, cl.x >> 16, cl.y & 0xffffu};
             bool sat = false;
 #pragma unroll
@@ -100,8 +86,8 @@ __device__ __noinline__ int index_rebuild(const IndexParams& p, unsigned* B, con
         if (lane == 0) {
             const int w = base >> 5;
             B[w] = b0;
-            B[p.bm_words + w] = b1;
-            B[2 * p.bm_words + w] = b2;
+            B[ix.bm_words + w] = b1;
+            B[2 * ix.bm_words + w] = b2;
         }
         n_live += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
     }
@@ -110,15 +96,15 @@ __device__ __noinline__ int index_rebuild(const IndexParams& p, unsigned* B, con
 }
 
 // What choice() returns for the current state: kind/lit as in SetInfo.
-__device__ __forceinline__ void index_choice(const IndexParams& p, const unsigned* B, const unsigned* table, int n_live,
+__device__ __forceinline__ void index_choice(const IndexRoot& ix, const unsigned* B, const unsigned* table, int n_live,
                                              unsigned lane, int& kind, int& lit) {
     if (n_live == 0) { kind = K_EMPTY; lit = 0; return; }
-    int c = bitmap_first(B + 2 * p.bm_words, p.bm_words, lane);
+    int c = bitmap_first(B + 2 * ix.bm_words, ix.bm_words, lane);
     const bool unit = c >= 0;
-    if (!unit) c = bitmap_first(B + p.bm_words, p.bm_words, lane);
+    if (!unit) c = bitmap_first(B + ix.bm_words, ix.bm_words, lane);
     if (c >= 0) {
         // the clause's literals that are still there (non-zero and unassigned); take the LAST one
-        const pclause cl = __ldg(&p.root[c]);
+        const pclause cl = __ldg(&ix.root[c]);
         const unsigned f = lane == 0 ? (cl.x & 0xffffu) : lane == 1 ? (cl.x >> 16) : (cl.y & 0xffffu);
         const bool there = lane < 3 && f != 0u && table_get(table, f >> 1) == 0u;
         const unsigned m = __ballot_sync(kFullMask, there);
@@ -129,57 +115,182 @@ __device__ __forceinline__ void index_choice(const IndexParams& p, const unsigne
         return;
     }
     // neither units nor one-zero clauses: |A[0].l[0]| (NDP:778-779)
-    c = bitmap_first(B, p.bm_words, lane);
+    c = bitmap_first(B, ix.bm_words, lane);
     kind = K_DECIDE;
-    if (p.first_zero3 >= 0 && (c < 0 || p.first_zero3 < c)) { lit = 0; return; }   // A[0] is {0,0,0}
-    const int l = code_lit(__ldg(&p.root[c]).x & 0xffffu);
+    if (ix.first_zero3 >= 0 && (c < 0 || ix.first_zero3 < c)) { lit = 0; return; }   // A[0] is {0,0,0}
+    const int l = code_lit(__ldg(&ix.root[c]).x & 0xffffu);
     lit = l < 0 ? -l : l;
 }
 
 // Resolution for "literal t becomes true".  kWrite applies it; otherwise it only classifies.
 // Returns the live count afterwards; conflict is raised when a clause reaches three zeros.
 template <bool kWrite>
-__device__ __forceinline__ int index_assign(const IndexParams& p, unsigned* B, int n_live, int t, bool& conflict,
+__device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, int n_live, int t, bool& conflict,
                                             unsigned lane) {
     const unsigned v = (unsigned)(t < 0 ? -t : t);
-    const unsigned a = __ldg(&p.occ_off[v]), b = __ldg(&p.occ_off[v + 1]);
+    const unsigned a = __ldg(&ix.occ_off[v]), b = __ldg(&ix.occ_off[v + 1]);
     int dropped = 0;
     bool confl = false;
     for (unsigned i = a + lane; i < b; i += 32) {
-        const unsigned e = __ldg(&p.occ[i]);
+        const unsigned e = __ldg(&ix.occ[i]);
         const unsigned c = e & 0xffffffu, n_pos = (e >> 24) & 3u, n_neg = (e >> 26) & 3u;
         const unsigned w = c >> 5, bit = 1u << (c & 31u);
         int k = -1;
         if (B[w] & bit) k = 0;
-        else if (B[p.bm_words + w] & bit) k = 1;
-        else if (B[2 * p.bm_words + w] & bit) k = 2;
+        else if (B[ix.bm_words + w] & bit) k = 1;
+        else if (B[2 * ix.bm_words + w] & bit) k = 2;
         if (k < 0) continue;   // already satisfied earlier on this path
         const unsigned n_true = t > 0 ? n_pos : n_neg, n_false = t > 0 ? n_neg : n_pos;
         if (n_true) {
             ++dropped;
-            if (kWrite) atomicAnd(&B[k * p.bm_words + w], ~bit);
+            if (kWrite) atomicAnd(&B[k * ix.bm_words + w], ~bit);
         } else {
             const int k2 = k + (int)n_false;
             if (k2 >= 3) confl = true;
             if (kWrite) {
-                atomicAnd(&B[k * p.bm_words + w], ~bit);
-                if (k2 < 3) atomicOr(&B[k2 * p.bm_words + w], bit);
+                atomicAnd(&B[k * ix.bm_words + w], ~bit);
+                if (k2 < 3) atomicOr(&B[k2 * ix.bm_words + w], bit);
             }
         }
     }
-    conflict = p.n_zero3 > 0 || __any_sync(kFullMask, confl);
+    conflict = ix.n_zero3 > 0 || __any_sync(kFullMask, confl);
     if (kWrite) __syncwarp();
     return n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
 }
 
+__device__ __forceinline__ void table_set(unsigned* table, int t) {
+    const unsigned v = (unsigned)(t < 0 ? -t : t);
+    table[v >> 4] |= (t > 0 ? 1u : 2u) << ((v & 15u) * 2u);
+}
+
+// copy one state slot (slot_words is a multiple of 4; both sides 16-byte aligned)
+__device__ __forceinline__ void slot_copy(unsigned* dst, const unsigned* src, int slot_words, unsigned lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = lane; i < slot_words / 4; i += 32) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// BFS level over state slots: one warp per node (Satisfy_iterative_BFS loop body, NDP:898-925).
+// The parent's slot is staged in shared memory, the branch is applied there, and an open child
+// (non-empty, conflict-free: NDP:908,919) is written to slot 2j (LA) / 2j+1 (RA) of the other
+// buffer together with what choice() returns for it.  Per-child metadata as in bfs_expand_kernel.
+__global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot ix, const unsigned* __restrict__ src,
+                                                               unsigned* __restrict__ dst,
+                                                               const BfsNode* __restrict__ nodes, int m,
+                                                               BfsChild* __restrict__ children) {
+    extern __shared__ __align__(16) unsigned smem_words[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps_per_block = blockDim.x >> 5;
+    unsigned* S = smem_words + (size_t)(threadIdx.x >> 5) * ix.slot_words;
+    unsigned* table = S + 3 * ix.bm_words;
+    for (int j = blockIdx.x * warps_per_block + (threadIdx.x >> 5); j < m; j += gridDim.x * warps_per_block) {
+        const BfsNode nd = nodes[j];
+        const unsigned* parent = src + (size_t)nd.slot * ix.slot_words;
+        BfsChild ch[2];
+        ch[0].n = ch[1].n = -1;
+        ch[0].kind = ch[1].kind = K_EMPTY;
+        ch[0].lit = ch[1].lit = 0;
+        ch[0].empty = ch[1].empty = 0;
+        const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+        if (nd.n > 0 && var != 0) {
+            for (int b = 0; b < 2; ++b) {
+                const int t = b == 0 ? var : -var;   // b=0: LA (i := true), b=1: RA (i := false)
+                if (nd.kind == K_UNIT && t != nd.lit) continue;   // falsifies the unit clause: {0,0,0}
+                __syncwarp();
+                slot_copy(S, parent, ix.slot_words, lane);
+                __syncwarp();
+                if (lane == 0) table_set(table, t);
+                bool conflict;
+                const int n_after = index_assign<true>(ix, S, nd.n, t, conflict, lane);
+                if (n_after == 0) ch[b].empty = 1;
+                if (n_after > 0 && !conflict) {
+                    int kind, lit;
+                    index_choice(ix, S, table, n_after, lane, kind, lit);
+                    ch[b].n = n_after; ch[b].kind = kind; ch[b].lit = lit;
+                    slot_copy(dst + ((size_t)2 * j + b) * ix.slot_words, S, ix.slot_words, lane);
+                }
+            }
+        }
+        if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
+    }
+}
+
+// State slots from assignment tables: one warp per slot.  tables[q] (table_words each) is copied
+// into the slot, the bitmaps are derived from it, and n/kind/lit are reported.  Used for the root
+// (empty table) and for frontiers that were not produced by the index BFS.
+__global__ void __launch_bounds__(128) index_states_kernel(const IndexRoot ix, const unsigned* __restrict__ tables,
+                                                           unsigned* __restrict__ slots, int count,
+                                                           BfsNode* __restrict__ meta) {
+    extern __shared__ __align__(16) unsigned smem_words[];
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps_per_block = blockDim.x >> 5;
+    unsigned* S = smem_words + (size_t)(threadIdx.x >> 5) * ix.slot_words;
+    unsigned* table = S + 3 * ix.bm_words;
+    for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block) {
+        __syncwarp();
+        for (int w = lane; w < ix.slot_words - 3 * ix.bm_words; w += 32)
+            table[w] = w < ix.table_words ? __ldg(&tables[(size_t)q * ix.table_words + w]) : 0u;
+        __syncwarp();
+        const int n_live = index_rebuild(ix, S, table, lane);
+        int kind, lit;
+        index_choice(ix, S, table, n_live, lane, kind, lit);
+        slot_copy(slots + (size_t)q * ix.slot_words, S, ix.slot_words, lane);
+        if (lane == 0) { BfsNode nn; nn.slot = (uint32_t)q; nn.n = n_live; nn.kind = kind; nn.lit = lit; meta[q] = nn; }
+    }
+}
+
+// Materialise clause lists: out[q] (stride records, tombstone-padded tail) = root filtered by the
+// table of state slot_ptr[q], in root order.  One warp per element.
+__global__ void __launch_bounds__(128) index_materialise_kernel(const IndexRoot ix,
+                                                                const unsigned* const* __restrict__ slot_ptr,
+                                                                int count, pclause* __restrict__ out, size_t stride,
+                                                                int32_t* __restrict__ out_n) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block) {
+        const unsigned* table = slot_ptr[q] + 3 * ix.bm_words;
+        SetInfo s = warp_rebuild<true>(ix.root, ix.n_root, out + (size_t)q * stride, table, lane);
+        if (lane == 0 && out_n) out_n[q] = s.n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DFS over state slots.  Persistent grid; a warp pulls the next subproblem of its shard, copies its
+// state slot into shared memory and runs the whole search there.  The explicit stack is the trail
+// (global memory) plus one pending bit per trail position; a popped LA sibling is re-derived from
+// (slot table + trail) with one pass over the root.
+struct IndexParams {
+    IndexRoot ix;
+    const unsigned* const* slot_ptr;  // [n_local] state slot of each subproblem
+    const BfsNode* meta;              // [n_local] n / kind / lit of each subproblem
+    int pend_words, trail_cap;
+    unsigned long long first, stride, n_local;
+    unsigned int* next;
+    unsigned long long* best;
+    unsigned long long* peer_best[8];
+    int n_peers;
+    int early_exit;
+    uint8_t* verdict;
+    unsigned long long* nodes;
+    unsigned long long* evals;
+    unsigned int* rebuilds;
+    unsigned long long* model_sub;    // [n_warps]
+    int32_t* model_len;               // [n_warps]
+    short* trails;                    // [n_warps][trail_cap] working trail of each warp
+    int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
+    int warp_bytes, off_pend;         // shared memory of one warp: state slot, then pend
+};
+
 __global__ void dfs_index_kernel(const IndexParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const IndexRoot& ix = p.ix;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = threadIdx.x >> 5;
     const unsigned gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* mine = smem_raw + (size_t)warp * p.warp_bytes;
     unsigned* B = reinterpret_cast<unsigned*>(mine);
-    unsigned* table = reinterpret_cast<unsigned*>(mine + p.off_table);
+    unsigned* table = B + 3 * ix.bm_words;
     unsigned* pend = reinterpret_cast<unsigned*>(mine + p.off_pend);
     short* trail = p.trails + (size_t)gwarp * p.trail_cap;
 
@@ -193,13 +304,13 @@ __global__ void dfs_index_kernel(const IndexParams p) {
             if (lane == 0) { p.verdict[q] = 2; p.nodes[q] = 0; p.evals[q] = 0; p.rebuilds[q] = 0; }
             continue;
         }
-        const unsigned* ptab = p.prefix_tables + (size_t)q * p.table_words;
-        for (int w = lane; w < p.table_words; w += 32) table[w] = __ldg(&ptab[w]);
-        for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
+        const unsigned* slot = p.slot_ptr[q];
         __syncwarp();
-        int n_live = index_rebuild(p, B, table, lane);
-        int kind, lit;
-        index_choice(p, B, table, n_live, lane, kind, lit);
+        slot_copy(B, slot, ix.slot_words, lane);
+        for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
+        const BfsNode nd = p.meta[q];
+        int n_live = nd.n, kind = nd.kind, lit = nd.lit;
+        __syncwarp();
         int ntrail = 0;
         unsigned long long nodes = 0, evals = 0;
         unsigned rebuilds = 0;
@@ -216,12 +327,12 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 t = lit;   // the other branch falsifies the unit clause: {0,0,0}, never pushed
             } else {
                 bool la_conf, ra_conf;
-                const int la_n = index_assign<false>(p, B, n_live, var, la_conf, lane);
+                const int la_n = index_assign<false>(ix, B, n_live, var, la_conf, lane);
                 if (la_n == 0) {                                    // LA empty wins first (NDP:843-850)
                     if (lane == 0) trail[ntrail] = (short)var;
                     ++ntrail; verdict = 1; break;
                 }
-                const int ra_n = index_assign<false>(p, B, n_live, -var, ra_conf, lane);
+                const int ra_n = index_assign<false>(ix, B, n_live, -var, ra_conf, lane);
                 if (ra_n == 0) {                                    // NDP:863-870
                     if (lane == 0) trail[ntrail] = (short)(-var);
                     ++ntrail; verdict = 1; break;
@@ -234,15 +345,14 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 if (lane == 0) {
                     if (pending) pend[ntrail >> 5] |= 1u << (ntrail & 31);
                     trail[ntrail] = (short)t;
-                    const unsigned v = (unsigned)(t < 0 ? -t : t);
-                    table[v >> 4] |= (t > 0 ? 1u : 2u) << ((v & 15u) * 2u);
+                    table_set(table, t);
                 }
                 ++ntrail;
                 bool conflict;
-                n_live = index_assign<true>(p, B, n_live, t, conflict, lane);
+                n_live = index_assign<true>(ix, B, n_live, t, conflict, lane);
                 if (n_live == 0) { verdict = 1; break; }            // empty branch => model (NDP:843-852 / 863-872)
                 if (conflict) dead = true;
-                else { index_choice(p, B, table, n_live, lane, kind, lit); continue; }
+                else { index_choice(ix, B, table, n_live, lane, kind, lit); continue; }
             }
             // Backtrack: pop to the deepest decision whose LA sibling is still pending.
             __syncwarp();
@@ -262,7 +372,7 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 trail[pos] = (short)(-trail[pos]);   // -i -> +i : now the LA sibling
             }
             ntrail = pos + 1;
-            for (int w = lane; w < p.table_words; w += 32) table[w] = __ldg(&ptab[w]);
+            for (int w = lane; w < ix.table_words; w += 32) table[w] = __ldg(&slot[3 * ix.bm_words + w]);
             __syncwarp();
             __threadfence_block();
             for (int j = lane; j < ntrail; j += 32) {
@@ -271,8 +381,8 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 atomicOr(&table[v >> 4], (l > 0 ? 1u : 2u) << ((v & 15u) * 2u));
             }
             __syncwarp();
-            n_live = index_rebuild(p, B, table, lane);
-            index_choice(p, B, table, n_live, lane, kind, lit);
+            n_live = index_rebuild(ix, B, table, lane);
+            index_choice(ix, B, table, n_live, lane, kind, lit);
             ++rebuilds;
         }
         if (verdict == 1) {
@@ -315,6 +425,17 @@ __global__ void prefix_table_kernel(const int32_t* __restrict__ entry_tree, cons
             row[v >> 4] |= (l > 0 ? 1u : 2u) << ((v & 15u) * 2u);
         }
     }
+}
+
+// One thread: the choices of one subproblem, leaf to root (the host reverses them).
+__global__ void tree_path_kernel(const int32_t* __restrict__ tree_parent, const int32_t* __restrict__ tree_lit,
+                                 int32_t leaf, int32_t* __restrict__ out, int cap, int32_t* __restrict__ out_len) {
+    int n = 0;
+    for (int32_t t = leaf; t > 0; t = tree_parent[t]) {
+        if (n < cap) out[n] = tree_lit[t];
+        ++n;
+    }
+    *out_len = n;
 }
 
 }  // namespace ndp

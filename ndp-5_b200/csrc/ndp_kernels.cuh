@@ -63,7 +63,8 @@ struct BfsLevelTotals {
     unsigned expanded;           // nodes that count as an iteration (choice() != 0, NDP:901-902, 926)
     unsigned long long evals;    // sum of |A| over those nodes
     unsigned max_n;              // largest child
-    unsigned pad[3];
+    unsigned stop_q;             // 1 iff the -q test "queue size >= Q before a pop" (NDP:894) fires inside this level
+    unsigned pad[2];
 };
 
 __global__ void __launch_bounds__(1024) bfs_compact_kernel(const BfsNode* __restrict__ nodes,
@@ -72,9 +73,11 @@ __global__ void __launch_bounds__(1024) bfs_compact_kernel(const BfsNode* __rest
                                                            BfsNode* __restrict__ next_nodes,
                                                            int32_t* __restrict__ next_tree,
                                                            int32_t* __restrict__ tree_parent,
-                                                           int32_t* __restrict__ tree_lit, int tree_base,
+                                                           int32_t* __restrict__ tree_lit, int tree_base, int Q,
                                                            BfsLevelTotals* __restrict__ totals) {
     __shared__ unsigned warp_count[32];
+    __shared__ unsigned stop_flag;
+    if (threadIdx.x == 0) stop_flag = 0u;
     __shared__ unsigned long long red_evals[32];
     __shared__ unsigned red_exp[32], red_max[32];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -97,11 +100,14 @@ __global__ void __launch_bounds__(1024) bfs_compact_kernel(const BfsNode* __rest
             if (w < (int)warp) before += c;
             total += c;
         }
+        const unsigned pos = running + before + __popc(bal & lt);   // open children before this one
+        // queue size just before node j is popped: the unexpanded rest of the level plus the
+        // children pushed so far
+        if (Q > 0 && idx < 2 * m && (idx & 1) == 0 && (unsigned)(m - (idx >> 1)) + pos >= (unsigned)Q) stop_flag = 1u;
         if (open) {
             const int j = idx >> 1;
             const BfsNode nd = nodes[j];
             const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
-            const unsigned pos = running + before + __popc(bal & lt);
             BfsNode nn;
             nn.slot = (uint32_t)idx;
             nn.n = ch.n;
@@ -129,7 +135,8 @@ __global__ void __launch_bounds__(1024) bfs_compact_kernel(const BfsNode* __rest
     if (tid == 0) {
         BfsLevelTotals t;
         t.m_next = running; t.expanded = 0; t.evals = 0; t.max_n = 0;
-        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+        t.stop_q = stop_flag;
+        t.pad[0] = t.pad[1] = 0;
         for (int w = 0; w < 32; ++w) { t.evals += red_evals[w]; t.expanded += red_exp[w]; t.max_n = max(t.max_n, red_max[w]); }
         *totals = t;
     }
