@@ -226,6 +226,19 @@ int ensure_arena(T*& p, size_t& cap, size_t slots, size_t slot_bytes) {
     return NDP_OK;
 }
 
+// grow a LIVE arena buffer (contents are kept)
+template <class T>
+int grow_arena_keep(T*& p, size_t& cap, size_t slots, size_t slot_bytes) {
+    if (cap >= slots) return NDP_OK;
+    T* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, slots * slot_bytes));
+    if (p && cap) CUDA_TRY(cudaMemcpy(q, p, cap * slot_bytes, cudaMemcpyDeviceToDevice));
+    if (p) cudaFree(p);
+    p = q;
+    cap = slots;
+    return NDP_OK;
+}
+
 // pack an int32 n x 3 clause array; returns false if a literal does not fit the 16-bit codes
 bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
     for (size_t k = 0; k < n; ++k) {
@@ -550,6 +563,46 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         st.tree_count = 1;
         f->h2d_bytes += sizeof root + 12;
     }
+    // trunk kernel (index engine): as many warps as state slots fit one CTA's shared memory, <= 32
+    int trunk_warps = 0;
+    bool trunk_ok = true;
+    volatile TrunkState* h_trunk = nullptr;
+    TrunkState* d_trunk = nullptr;
+    struct HostFree { void* p = nullptr; ~HostFree() { if (p) cudaFreeHost(p); } } trunk_mem;
+    if (use_index && !getenv("NDP_NO_TRUNK")) {
+        trunk_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
+        if (trunk_warps >= 2) {
+            CUDA_TRY(cudaHostAlloc(&trunk_mem.p, sizeof(TrunkState), cudaHostAllocMapped));
+            h_trunk = static_cast<volatile TrunkState*>(trunk_mem.p);
+            CUDA_TRY(cudaHostGetDevicePointer((void**)&d_trunk, trunk_mem.p, 0));
+            CUDA_TRY(cudaFuncSetAttribute(bfs_index_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(trunk_warps * slot_bytes)));
+        } else trunk_warps = 0;
+    }
+    // persistent level loop (index engine): cooperative launch, one CTA per SM
+    bool persist_ok = false, persist_rearm = false;
+    size_t persist_cap = 0;
+    DevBuf d_pstate;
+    int coop_grid = 0;
+    if (use_index && !getenv("NDP_NO_PERSIST")) {
+        int coop = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+        if (coop && 8 * slot_bytes <= 200 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(bfs_index_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(8 * slot_bytes)));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_index_persistent_kernel, 256, 8 * slot_bytes));
+            if (per_sm >= 1) {
+                coop_grid = sms * std::min(per_sm, 2);
+                CUDA_TRY(cudaMalloc(&d_pstate.p, sizeof(PersistState)));
+                persist_ok = true;
+                const size_t budget = ((size_t)4 << 30) / slot_bytes;   // <= 4 GB per buffer up front
+                persist_cap = Q > 0 ? std::min<size_t>(2 * (size_t)Q, budget) : std::min<size_t>(8192, budget);
+                persist_cap = std::max<size_t>(persist_cap, 64);
+            }
+        }
+    }
     cudaEvent_t ev_loop0, ev_loop1;        // device timeline of the whole level loop
     CUDA_TRY(cudaEventCreate(&ev_loop0));
     CUDA_TRY(cudaEventCreate(&ev_loop1));
@@ -579,6 +632,87 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         // can any stop test fire inside this level?  -q: the queue never exceeds m + pushes <= 2m;
         // -d: the level is consumed whole iff it + m < D.
         const bool safe = !stop_at_top && (Q > 0 ? 2 * m < (size_t)Q : (it + (long long)m < (long long)D));
+        if (use_index && safe && trunk_warps > 0 && m <= (size_t)trunk_warps && trunk_ok) {
+            // narrow levels: one CTA runs level after level on the device (bfs_index_trunk_kernel)
+            const int max_levels = 4096;
+            if ((status = ensure_arena(f->sbuf[cur_buf ^ 1], f->scap_slots[cur_buf ^ 1], 64, slot_bytes))) break;
+            if ((status = st.reserve_nodes(64)) || (status = st.reserve_tree(st.tree_count + (size_t)max_levels * 64))) break;
+            TrunkState ts;
+            ts.m = (int)m; ts.cur = st.cur; ts.cur_buf = cur_buf; ts.levels_done = 0;
+            ts.it = it; ts.task_count = task_count; ts.evals = 0; ts.tree_count = (unsigned)st.tree_count; ts.pad = 0;
+            memcpy((void*)h_trunk, &ts, sizeof ts);
+            bfs_index_trunk_kernel<<<1, trunk_warps * 32, (size_t)trunk_warps * slot_bytes>>>(
+                *ix, f->sbuf[0], f->sbuf[1], st.nodes[0], st.nodes[1], st.node_tree[0], st.node_tree[1], st.tree_parent,
+                st.tree_lit, D, Q, max_levels, d_trunk);
+            cudaError_t te = cudaStreamSynchronize(0);
+            if (te != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS trunk: ") + cudaGetErrorString(te)); break; }
+            memcpy(&ts, (const void*)h_trunk, sizeof ts);
+            f->bfs_launches += 1;
+            f->d2h_bytes += sizeof ts;
+            f->h2d_bytes += sizeof ts;
+            trunk_ok = false;                 // re-armed after the next regular level
+            if (ts.levels_done > 0) {
+                m = (size_t)ts.m; st.cur = ts.cur; cur_buf = ts.cur_buf;
+                it = ts.it; task_count = ts.task_count; f->bfs_evals += ts.evals; st.tree_count = ts.tree_count;
+                n_safe += (size_t)ts.levels_done;
+                t_safe += now_ms() - t_level;
+                continue;
+            }
+        }
+        trunk_ok = true;
+        if (persist_ok && !stop_at_top && (Q > 0 || it + (long long)m < (long long)D)) {
+            // hand the level loop to the device until a stop level, an empty queue or a full arena
+            if (2 * m > persist_cap) persist_cap = std::max(persist_cap * 2, 4 * m);
+            if ((status = grow_arena_keep(f->sbuf[cur_buf], f->scap_slots[cur_buf], persist_cap, slot_bytes))) break;
+            status = ensure_arena(f->sbuf[cur_buf ^ 1], f->scap_slots[cur_buf ^ 1], persist_cap, slot_bytes);
+            if (status == NDP_E_NOMEM) { cudaGetLastError(); g_err.clear(); status = NDP_OK; persist_ok = false; }
+            if (status) break;
+            if (persist_ok) {
+                const size_t tree_room = std::max<size_t>(16 * persist_cap, (size_t)4 << 20);
+                if ((status = st.reserve_nodes(persist_cap)) || (status = st.reserve_tree(st.tree_count + tree_room))) break;
+                PersistState ps;
+                memset(&ps, 0, sizeof ps);
+                ps.m = (int)m; ps.cur = st.cur; ps.cur_buf = cur_buf;
+                ps.it = it; ps.task_count = task_count; ps.tree_count = st.tree_count;
+                ps.cap_slots = std::min(f->scap_slots[0], f->scap_slots[1]);
+                ps.cap_nodes = st.node_cap;
+                ps.cap_tree = st.tree_cap;
+                CUDA_TRY(cudaMemcpy(d_pstate.p, &ps, sizeof ps, cudaMemcpyHostToDevice));
+                IndexRoot ixv = *ix;
+                unsigned *a0 = f->sbuf[0], *a1 = f->sbuf[1];
+                BfsNode *n0 = st.nodes[0], *n1 = st.nodes[1];
+                int32_t *t0 = st.node_tree[0], *t1 = st.node_tree[1], *tp = st.tree_parent, *tl = st.tree_lit;
+                BfsChild* chd = st.children;
+                int Dv = D, Qv = Q, ovrv = ovr ? 1 : 0, maxl = 1 << 20;
+                PersistState* dps = d_pstate.as<PersistState>();
+                void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps};
+                cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid), dim3(256),
+                                                             args, 8 * slot_bytes, 0);
+                if (le == cudaSuccess) le = cudaStreamSynchronize(0);
+                if (le != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS persistent kernel: ") + cudaGetErrorString(le)); break; }
+                CUDA_TRY(cudaMemcpy(&ps, d_pstate.p, sizeof ps, cudaMemcpyDeviceToHost));
+                f->bfs_launches += 1;
+                f->h2d_bytes += sizeof ps;
+                f->d2h_bytes += sizeof ps;
+                if (ps.m < 0) ps.m = -ps.m;   // stop level left untouched for the exact walk below
+                m = (size_t)ps.m; st.cur = ps.cur; cur_buf = ps.cur_buf;
+                it = ps.it; task_count = ps.task_count; f->bfs_evals += ps.evals; st.tree_count = ps.tree_count;
+                n_safe += (size_t)ps.levels_done;
+                t_safe += now_ms() - t_level;
+                if (ps.exit_reason == PEXIT_CAPACITY) {
+                    // the choice tree is simply re-reserved on re-entry; slots / node lists grow here
+                    if (2 * m > persist_cap) {
+                        const size_t bound = Q > 0 ? 2 * (size_t)Q : SIZE_MAX;
+                        persist_cap = std::min(std::max(persist_cap * 2, 4 * m), std::max(bound, 2 * m));
+                    }
+                    continue;
+                }
+                if (ps.exit_reason == PEXIT_EMPTY || ps.exit_reason == PEXIT_LEVELS) continue;
+                persist_ok = false;            // PEXIT_HOST_LEVEL: this level goes through the exact per-level path
+                persist_rearm = true;
+                continue;
+            }
+        }
         if (stop_at_top) {
             if ((status = st.download_level(m, h_nodes, h_node_tree, f->d2h_bytes))) break;
             for (size_t j = 0; j < m; ++j)
@@ -637,6 +771,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
             m = tot.m_next;
             t_safe += now_ms() - t_level;
             ++n_safe;
+            if (persist_rearm) { persist_ok = true; persist_rearm = false; }
             continue;
         }
         // a stop test can fire here: walk the level on the host with the exact rules

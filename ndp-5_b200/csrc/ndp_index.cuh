@@ -24,6 +24,8 @@
 // and reaching three zeros is the conflict.  The materialised clause list of a node (needed only
 // for -s JSON, ndp_frontier_get and the scan engine) is the root filtered by its table.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ndp_clause.cuh"
 #include "ndp_kernels.cuh"
 
@@ -169,12 +171,52 @@ __device__ __forceinline__ void slot_copy(unsigned* dst, const unsigned* src, in
     uint4* d = reinterpret_cast<uint4*>(dst);
     for (int i = lane; i < slot_words / 4; i += 32) d[i] = s[i];
 }
+// same, reading the source through L2 only (.cg): used where another SM may have written the slot
+// earlier in the same launch
+__device__ __forceinline__ void slot_load_cg(unsigned* dst_shared, const unsigned* src, int slot_words, unsigned lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst_shared);
+    for (int i = lane; i < slot_words / 4; i += 32) d[i] = __ldcg(&s[i]);
+}
 
 // ------------------------------------------------------------------------------------------
 // BFS level over state slots: one warp per node (Satisfy_iterative_BFS loop body, NDP:898-925).
 // The parent's slot is staged in shared memory, the branch is applied there, and an open child
 // (non-empty, conflict-free: NDP:908,919) is written to slot 2j (LA) / 2j+1 (RA) of the other
 // buffer together with what choice() returns for it.  Per-child metadata as in bfs_expand_kernel.
+// One node: stage the parent's slot in S (shared), apply each attempted branch, write open
+// children to dst slots 2j / 2j+1.  ch[0] = LA, ch[1] = RA.
+__device__ __forceinline__ void index_expand_node(const IndexRoot& ix, const unsigned* src,   // no __restrict__:
+                                                  unsigned* dst, int j, const BfsNode nd, unsigned* S,   // the trunk kernel re-reads what it wrote
+
+                                                  unsigned lane, BfsChild ch[2]) {
+    unsigned* table = S + 3 * ix.bm_words;
+    const unsigned* parent = src + (size_t)nd.slot * ix.slot_words;
+    ch[0].n = ch[1].n = -1;
+    ch[0].kind = ch[1].kind = K_EMPTY;
+    ch[0].lit = ch[1].lit = 0;
+    ch[0].empty = ch[1].empty = 0;
+    const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+    if (nd.n <= 0 || var == 0) return;
+    for (int b = 0; b < 2; ++b) {
+        const int t = b == 0 ? var : -var;   // b=0: LA (i := true), b=1: RA (i := false)
+        if (nd.kind == K_UNIT && t != nd.lit) continue;   // falsifies the unit clause: {0,0,0}
+        __syncwarp();
+        slot_load_cg(S, parent, ix.slot_words, lane);
+        __syncwarp();
+        if (lane == 0) table_set(table, t);
+        bool conflict;
+        const int n_after = index_assign<true>(ix, S, nd.n, t, conflict, lane);
+        if (n_after == 0) ch[b].empty = 1;
+        if (n_after > 0 && !conflict) {
+            int kind, lit;
+            index_choice(ix, S, table, n_after, lane, kind, lit);
+            ch[b].n = n_after; ch[b].kind = kind; ch[b].lit = lit;
+            slot_copy(dst + ((size_t)2 * j + b) * ix.slot_words, S, ix.slot_words, lane);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot ix, const unsigned* __restrict__ src,
                                                                unsigned* __restrict__ dst,
                                                                const BfsNode* __restrict__ nodes, int m,
@@ -183,36 +225,265 @@ __global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot i
     const unsigned lane = threadIdx.x & 31u;
     const int warps_per_block = blockDim.x >> 5;
     unsigned* S = smem_words + (size_t)(threadIdx.x >> 5) * ix.slot_words;
-    unsigned* table = S + 3 * ix.bm_words;
     for (int j = blockIdx.x * warps_per_block + (threadIdx.x >> 5); j < m; j += gridDim.x * warps_per_block) {
-        const BfsNode nd = nodes[j];
-        const unsigned* parent = src + (size_t)nd.slot * ix.slot_words;
         BfsChild ch[2];
-        ch[0].n = ch[1].n = -1;
-        ch[0].kind = ch[1].kind = K_EMPTY;
-        ch[0].lit = ch[1].lit = 0;
-        ch[0].empty = ch[1].empty = 0;
-        const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
-        if (nd.n > 0 && var != 0) {
-            for (int b = 0; b < 2; ++b) {
-                const int t = b == 0 ? var : -var;   // b=0: LA (i := true), b=1: RA (i := false)
-                if (nd.kind == K_UNIT && t != nd.lit) continue;   // falsifies the unit clause: {0,0,0}
-                __syncwarp();
-                slot_copy(S, parent, ix.slot_words, lane);
-                __syncwarp();
-                if (lane == 0) table_set(table, t);
-                bool conflict;
-                const int n_after = index_assign<true>(ix, S, nd.n, t, conflict, lane);
-                if (n_after == 0) ch[b].empty = 1;
-                if (n_after > 0 && !conflict) {
-                    int kind, lit;
-                    index_choice(ix, S, table, n_after, lane, kind, lit);
-                    ch[b].n = n_after; ch[b].kind = kind; ch[b].lit = lit;
-                    slot_copy(dst + ((size_t)2 * j + b) * ix.slot_words, S, ix.slot_words, lane);
+        index_expand_node(ix, src, dst, j, nodes[j], S, lane, ch);
+        if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
+    }
+}
+
+// The narrow "trunk" of a granulation: while a level has at most W = blockDim/32 nodes and no
+// stop test can fire in it (-q: 2m < Q; -d: it + m < D), ONE CTA runs level after level without
+// returning to the host: a warp per node, the level's children compacted by warp 0 between two
+// __syncthreads.  (For the multiplier CNFs roughly 60 levels pass per doubling of the width, so
+// a third to a half of all levels live here.)  State in/out through `st`.
+struct TrunkState {
+    int m, cur, cur_buf, levels_done;
+    long long it, task_count;
+    unsigned long long evals;
+    unsigned tree_count, pad;
+};
+
+__global__ void __launch_bounds__(1024) bfs_index_trunk_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
+                                                               BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
+                                                               int32_t* ntree1, int32_t* __restrict__ tree_parent,
+                                                               int32_t* __restrict__ tree_lit, int D, int Q,
+                                                               int max_levels, TrunkState* st_io) {
+    extern __shared__ __align__(16) unsigned smem_words[];
+    __shared__ TrunkState st;
+    __shared__ BfsChild sch[64];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    unsigned* S = smem_words + (size_t)warp * ix.slot_words;
+    if (threadIdx.x == 0) st = *st_io;
+    __syncthreads();
+    for (int level = 0; level < max_levels; ++level) {
+        const int m = st.m;
+        const bool safe = Q > 0 ? 2 * (long long)m < (long long)Q : st.it + m < (long long)D;
+        if (m == 0 || m > W || !safe) break;
+        unsigned* src = st.cur_buf ? sbuf1 : sbuf0;
+        unsigned* dst = st.cur_buf ? sbuf0 : sbuf1;
+        const BfsNode* nodes = st.cur ? nodes1 : nodes0;
+        const int32_t* ntree = st.cur ? ntree1 : ntree0;
+        BfsNode* nnodes = st.cur ? nodes0 : nodes1;
+        int32_t* nntree = st.cur ? ntree0 : ntree1;
+        if ((int)warp < m) {
+            BfsChild ch[2];
+            index_expand_node(ix, src, dst, (int)warp, nodes[warp], S, lane, ch);
+            if (lane == 0) { sch[2 * warp] = ch[0]; sch[2 * warp + 1] = ch[1]; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // queue order: children of node 0 first, LA before RA (NDP:904-925)
+            unsigned running = 0, expanded = 0;
+            unsigned long long evals = 0;
+            const unsigned lt = lanemask_lt();
+            for (int base = 0; base < 2 * m; base += 32) {
+                const int idx = base + (int)lane;
+                const bool open = idx < 2 * m && sch[idx].n >= 0;
+                const unsigned bal = __ballot_sync(kFullMask, open);
+                if (open) {
+                    const int j = idx >> 1;
+                    const BfsNode nd = nodes[j];
+                    const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+                    const unsigned pos = running + __popc(bal & lt);
+                    BfsNode nn;
+                    nn.slot = (uint32_t)idx; nn.n = sch[idx].n; nn.kind = sch[idx].kind; nn.lit = sch[idx].lit;
+                    nnodes[pos] = nn;
+                    nntree[pos] = (int32_t)(st.tree_count + pos);
+                    tree_parent[st.tree_count + pos] = ntree[j];
+                    tree_lit[st.tree_count + pos] = (idx & 1) ? -var : var;
+                }
+                running += __popc(bal);
+            }
+            for (int j = (int)lane; j < m; j += 32) {
+                const BfsNode nd = nodes[j];
+                const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+                if (nd.n > 0 && var != 0) { evals += (unsigned long long)nd.n; ++expanded; }
+            }
+            for (int off = 16; off > 0; off >>= 1) evals += __shfl_down_sync(kFullMask, evals, off);
+            expanded = __reduce_add_sync(kFullMask, expanded);
+            if (lane == 0) {
+                st.it += expanded;                 // NDP:926
+                st.task_count += running;          // NDP:912,923
+                st.evals += evals;
+                st.tree_count += running;
+                st.cur ^= 1;
+                st.cur_buf ^= 1;
+                st.m = (int)running;
+                st.levels_done += 1;
+            }
+        }
+        __threadfence();   // next level's warps read the nodes / slots / tree written above
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *st_io = st;
+}
+
+// The whole level loop on the device (cooperative launch, one CTA per SM): every level is
+//   expand   one warp per node, grid-stride (index_expand_node)            -> children metadata
+//   grid.sync
+//   compact  CTA 0: block-wide scan of the open flags -> next node list, choice tree, counters,
+//            and the exact -q test "queue size >= Q before a pop" (NDP:894) at every node
+//   grid.sync
+// and the kernel returns to the host only when it has to: the level in which a stop test fires
+// (left UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
+enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4 };
+struct PersistState {
+    int m, cur, cur_buf, levels_done, exit_reason, pad0;
+    long long it, task_count;
+    unsigned long long evals;
+    unsigned long long tree_count;
+    // capacities (set by the host)
+    unsigned long long cap_slots, cap_nodes, cap_tree;
+};
+
+__global__ void __launch_bounds__(256) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
+                                                                   BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
+                                                                   int32_t* ntree1, BfsChild* children,
+                                                                   int32_t* tree_parent, int32_t* tree_lit, int D, int Q,
+                                                                   int ovr, int max_levels, PersistState* st) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned smem_words[];
+    __shared__ unsigned warp_count[8];
+    __shared__ unsigned long long red_evals[8];
+    __shared__ unsigned red_exp[8];
+    __shared__ unsigned stop_flag, s_running;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int total_warps = gridDim.x * warps_per_block;
+    const int gwarp = blockIdx.x * warps_per_block + (int)warp;
+    unsigned* S = smem_words + (size_t)warp * ix.slot_words;
+    const unsigned lt = lanemask_lt();
+
+    for (int level = 0;; ++level) {
+        // every thread reads the same committed state (written before the last grid.sync)
+        const int m = __ldcg(&st->m), cur = __ldcg(&st->cur), cur_buf = __ldcg(&st->cur_buf);
+        const long long it = __ldcg(&st->it);
+        const unsigned long long tree_count = __ldcg(&st->tree_count);
+        int reason = PEXIT_NONE;
+        if (m == 0) reason = PEXIT_EMPTY;
+        else if ((Q > 0 && m >= Q) || (D == -1 && !ovr)) reason = PEXIT_HOST_LEVEL;          // NDP:894-897 at the level's first pop
+        else if (Q <= 0 && it + m >= (long long)D) reason = PEXIT_HOST_LEVEL;                // the -d budget ends inside this level
+        else if (2ull * m > __ldcg(&st->cap_slots) || 2ull * m > __ldcg(&st->cap_nodes) ||
+                 tree_count + 2ull * m > __ldcg(&st->cap_tree)) reason = PEXIT_CAPACITY;
+        else if (level >= max_levels) reason = PEXIT_LEVELS;
+        if (reason != PEXIT_NONE) {
+            if (blockIdx.x == 0 && tid == 0) st->exit_reason = reason;
+            return;   // uniform across the grid: every thread took the same decision from the same state
+        }
+        unsigned* src = cur_buf ? sbuf1 : sbuf0;
+        unsigned* dst = cur_buf ? sbuf0 : sbuf1;
+        BfsNode* nodes = cur ? nodes1 : nodes0;
+        int32_t* ntree = cur ? ntree1 : ntree0;
+        BfsNode* nnodes = cur ? nodes0 : nodes1;
+        int32_t* nntree = cur ? ntree0 : ntree1;
+        // ---- expand
+        for (int j = gwarp; j < m; j += total_warps) {
+            BfsNode nd;
+            {
+                const int4 raw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
+                nd.slot = (uint32_t)raw.x; nd.n = raw.y; nd.kind = raw.z; nd.lit = raw.w;
+            }
+            BfsChild ch[2];
+            index_expand_node(ix, src, dst, j, nd, S, lane, ch);
+            if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
+        }
+        grid.sync();
+        // ---- compact (CTA 0)
+        if (blockIdx.x == 0) {
+            if (tid == 0) { stop_flag = 0u; s_running = 0u; }
+            __syncthreads();
+            // Four children per thread and step (two whole nodes), the next step's metadata
+            // prefetched while this one is scanned: the walk is serial in `running` only.
+            unsigned running = 0;
+            const int step = 4 * (int)blockDim.x;
+            int4 nxt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = 4 * (int)tid + u;
+                nxt[u] = idx < 2 * m ? __ldcg(reinterpret_cast<const int4*>(&children[idx])) : make_int4(-1, 0, 0, 0);
+            }
+            for (int base = 0; base < 2 * m; base += step) {
+                int4 raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) raw[u] = nxt[u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + step + 4 * (int)tid + u;
+                    nxt[u] = idx < 2 * m ? __ldcg(reinterpret_cast<const int4*>(&children[idx])) : make_int4(-1, 0, 0, 0);
+                }
+                unsigned cnt = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cnt += raw[u].x >= 0 ? 1u : 0u;
+                unsigned incl = cnt;   // inclusive warp scan of the per-thread counts
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned v = __shfl_up_sync(kFullMask, incl, off);
+                    if ((int)lane >= off) incl += v;
+                }
+                if (lane == 31) warp_count[warp] = incl;
+                __syncthreads();
+                unsigned before = 0, total = 0;
+                for (int w = 0; w < warps_per_block; ++w) {
+                    const unsigned c = warp_count[w];
+                    if (w < (int)warp) before += c;
+                    total += c;
+                }
+                unsigned pos = running + before + incl - cnt;   // open children before this thread's first one
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + 4 * (int)tid + u;
+                    if (Q > 0 && idx < 2 * m && (u & 1) == 0 && (unsigned)(m - (idx >> 1)) + pos >= (unsigned)Q) stop_flag = 1u;
+                    if (raw[u].x >= 0) {
+                        const int j = idx >> 1;
+                        const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
+                        const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
+                        BfsNode nn;
+                        nn.slot = (uint32_t)idx; nn.n = raw[u].x; nn.kind = raw[u].y; nn.lit = raw[u].z;
+                        nnodes[pos] = nn;
+                        nntree[pos] = (int32_t)(tree_count + pos);
+                        tree_parent[tree_count + pos] = __ldcg(&ntree[j]);
+                        tree_lit[tree_count + pos] = (idx & 1) ? -var : var;
+                        ++pos;
+                    }
+                }
+                running += total;
+                __syncthreads();
+            }
+            unsigned long long evals = 0;
+            unsigned expanded = 0;
+            for (int j = (int)tid; j < m; j += (int)blockDim.x) {
+                const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
+                const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
+                if (nraw.y > 0 && var != 0) { evals += (unsigned long long)nraw.y; ++expanded; }
+            }
+            for (int off = 16; off > 0; off >>= 1) evals += __shfl_down_sync(kFullMask, evals, off);
+            expanded = __reduce_add_sync(kFullMask, expanded);
+            if (lane == 0) { red_evals[warp] = evals; red_exp[warp] = expanded; }
+            __syncthreads();
+            if (tid == 0) {
+                if (stop_flag) {
+                    st->exit_reason = PEXIT_HOST_LEVEL;   // a -q stop fires inside this level: leave it to the host
+                    st->m = -m;                            // sentinel: negative m makes every thread leave below
+                } else {
+                    unsigned long long ev = 0;
+                    unsigned ex = 0;
+                    for (int w = 0; w < warps_per_block; ++w) { ev += red_evals[w]; ex += red_exp[w]; }
+                    st->it = it + ex;                      // NDP:926
+                    st->task_count += running;             // NDP:912,923
+                    st->evals += ev;
+                    st->tree_count = tree_count + running;
+                    st->cur = cur ^ 1;
+                    st->cur_buf = cur_buf ^ 1;
+                    st->m = (int)running;
+                    st->levels_done += 1;
                 }
             }
         }
-        if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
+        grid.sync();
+        if (__ldcg(&st->m) < 0) return;   // stop level (the host restores m = -m); uniform across the grid
     }
 }
 
