@@ -1,0 +1,95 @@
+"""The N>1 host logic (static interleaved shards, verdict all-gather, lowest-winner reduction,
+model broadcast) over gloo with world_size 2 and 3 on the CPU.  The per-shard verdicts come from
+the oracle here (no GPU in this suite); on the GPU box the same functions run over NCCL in
+bench.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools"), os.path.join(ROOT, "ndp-5_b200", "py")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, case, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ndp_shard", os.path.join(ROOT, "ndp-5_b200", "py", "ndp5_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    import cbind
+    import gen_cnf
+    orc = cbind.OracleLib()
+    name, D, ovr, Q = case
+    A = orc.parse(gen_cnf.dimacs_text(*gen_cnf.NAMED[name]))
+    fr = orc.bfs(A, D, ovr, Q)["frontier"]          # every rank derives the same frontier (NDP:1651)
+    n = len(fr)
+    verdict = np.full(n, shard.NOT_RUN, dtype=np.uint8)
+    winner, model = None, None
+    for k in shard.shard_indices(n, rank, world):   # this rank's shard only
+        r = orc.dfs(fr[k][0])
+        verdict[k] = 1 if r["models"] else 0
+        if r["models"] and winner is None:
+            winner, model = int(k), np.concatenate([fr[k][1], r["model"]])
+    merged = shard.gather_verdicts(dist, verdict, n, rank, world)
+    gw = shard.lowest_winner(dist, winner, world)
+    gm = shard.broadcast_model(dist, model if winner == gw else None, gw, world)
+    total = shard.all_sum(dist, [int((verdict == 1).sum())], world)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), merged=merged, winner=-1 if gw is None else gw,
+             model=np.zeros(0, np.int32) if gm is None else gm, n_sat=total[0])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", [("rsaFACT-16bit", 2240, False, -1), ("prime-16bit", 0, True, 64),
+                                  ("rsaFACT-12bit", 0, True, 16)])
+def test_sharded_run_equals_single_rank(world, case, tmp_path, oracle, cnf_text):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    name, D, ovr, Q = case
+    fr = oracle.bfs(oracle.parse(cnf_text(name)), D, ovr, Q)["frontier"]
+    want, first = [], None
+    for k, (cl, ch) in enumerate(fr):
+        r = oracle.dfs(cl)
+        want.append(1 if r["models"] else 0)
+        if r["models"] and first is None:
+            first = (k, np.concatenate([ch, r["model"]]).tolist())
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        assert z["merged"].tolist() == want
+        assert int(z["n_sat"]) == sum(want)
+        if first is None:
+            assert int(z["winner"]) == -1 and z["model"].size == 0
+        else:
+            assert int(z["winner"]) == first[0] and z["model"].tolist() == first[1]
+
+
+def test_shard_indices_partition():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ndp_shard", os.path.join(ROOT, "ndp-5_b200", "py", "ndp5_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    for n in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            allidx = np.concatenate([shard.shard_indices(n, r, world) for r in range(world)])
+            assert sorted(allidx.tolist()) == list(range(n))
+    assert shard.gather_verdicts(None, [0, 1, 2], 3, 0, 1).tolist() == [0, 1, 2]
+    assert shard.lowest_winner(None, 5, 1) == 5 and shard.lowest_winner(None, None, 1) is None
