@@ -42,6 +42,27 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
     } while (0)
 
+// Device memory comes from the stream-ordered pool of the current device (all work of this
+// library runs on the legacy default stream): repeated BFS/DFS calls stop paying cudaMalloc /
+// cudaFree (the latter synchronises the device) for their arenas and per-call buffers.
+template <class T>
+cudaError_t dev_alloc(T** p, size_t bytes) {
+    static thread_local int tuned_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (tuned_device != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned_device = dev;
+    }
+    return cudaMallocAsync((void**)p, bytes ? bytes : 1, 0);
+}
+template <class T>
+cudaError_t dev_free(T* p) { return p ? cudaFreeAsync((void*)p, 0) : cudaSuccess; }
+
 int requested_engine() {
     int e = g_engine;
     if (e == NDP_ENGINE_AUTO) {
@@ -83,7 +104,7 @@ bool tracing() { static const bool t = getenv("NDP_TRACE") != nullptr; return t;
 
 struct DevBuf {  // tiny RAII for per-call device allocations
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) dev_free(p); }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
@@ -174,30 +195,30 @@ struct ndp_frontier {
     ~ndp_frontier() {
         for (auto& r : replicas) {
             cudaSetDevice(r.device);
-            if (r.shard_buf) cudaFree(r.shard_buf);
-            if (r.d_base) cudaFree((void*)r.d_base);
-            if (r.d_n) cudaFree(r.d_n);
+            if (r.shard_buf) dev_free(r.shard_buf);
+            if (r.d_base) dev_free((void*)r.d_base);
+            if (r.d_n) dev_free(r.d_n);
         }
         for (auto& r : index_replicas) {
             cudaSetDevice(r.device);
-            if (r.own_slots) cudaFree(r.own_slots);
-            if (r.d_slot_ptr) cudaFree((void*)r.d_slot_ptr);
-            if (r.d_meta) cudaFree(r.d_meta);
+            if (r.own_slots) dev_free(r.own_slots);
+            if (r.d_slot_ptr) dev_free((void*)r.d_slot_ptr);
+            if (r.d_meta) dev_free(r.d_meta);
         }
         for (auto& r : root_indexes) {
             cudaSetDevice(r.device);
-            if (r.d_root) cudaFree(r.d_root);
-            if (r.d_occ_off) cudaFree(r.d_occ_off);
-            if (r.d_occ) cudaFree(r.d_occ);
+            if (r.d_root) dev_free(r.d_root);
+            if (r.d_occ_off) dev_free(r.d_occ_off);
+            if (r.d_occ) dev_free(r.d_occ);
         }
         cudaSetDevice(device);
-        if (d_tree_parent) cudaFree(d_tree_parent);
-        if (d_tree_lit) cudaFree(d_tree_lit);
-        if (d_get) cudaFree(d_get);
-        if (d_get_ptr) cudaFree((void*)d_get_ptr);
+        if (d_tree_parent) dev_free(d_tree_parent);
+        if (d_tree_lit) dev_free(d_tree_lit);
+        if (d_get) dev_free(d_get);
+        if (d_get_ptr) dev_free((void*)d_get_ptr);
         for (int b = 0; b < 2; ++b) {
-            if (buf[b]) cudaFree(buf[b]);
-            if (sbuf[b]) cudaFree(sbuf[b]);
+            if (buf[b]) dev_free(buf[b]);
+            if (sbuf[b]) dev_free(sbuf[b]);
         }
     }
 };
@@ -219,9 +240,9 @@ int check_device() {
 template <class T>
 int ensure_arena(T*& p, size_t& cap, size_t slots, size_t slot_bytes) {
     if (cap >= slots) return NDP_OK;
-    if (p) { CUDA_TRY(cudaFree(p)); p = nullptr; cap = 0; }
+    if (p) { CUDA_TRY(dev_free(p)); p = nullptr; cap = 0; }
     const size_t want = std::max(slots, (size_t)64);
-    CUDA_TRY(cudaMalloc(&p, want * slot_bytes));
+    CUDA_TRY(dev_alloc(&p, want * slot_bytes));
     cap = want;
     return NDP_OK;
 }
@@ -231,9 +252,9 @@ template <class T>
 int grow_arena_keep(T*& p, size_t& cap, size_t slots, size_t slot_bytes) {
     if (cap >= slots) return NDP_OK;
     T* q = nullptr;
-    CUDA_TRY(cudaMalloc(&q, slots * slot_bytes));
+    CUDA_TRY(dev_alloc(&q, slots * slot_bytes));
     if (p && cap) CUDA_TRY(cudaMemcpy(q, p, cap * slot_bytes, cudaMemcpyDeviceToDevice));
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = q;
     cap = slots;
     return NDP_OK;
@@ -293,9 +314,9 @@ int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
         off[(size_t)V + 1] = (unsigned)occ.size();
     }
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMalloc(&r.d_root, root.size() * sizeof(pclause)));
-    CUDA_TRY(cudaMalloc(&r.d_occ_off, off.size() * 4));
-    CUDA_TRY(cudaMalloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
+    CUDA_TRY(dev_alloc(&r.d_root, root.size() * sizeof(pclause)));
+    CUDA_TRY(dev_alloc(&r.d_occ_off, off.size() * 4));
+    CUDA_TRY(dev_alloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
     CUDA_TRY(cudaMemcpy(r.d_root, root.data(), root.size() * sizeof(pclause), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r.d_occ_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
     if (!occ.empty()) CUDA_TRY(cudaMemcpy(r.d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
@@ -326,9 +347,9 @@ struct BfsLevelState {
 
     template <class T> static int grow(T*& p, size_t old_n, size_t new_n) {
         T* q = nullptr;
-        CUDA_TRY(cudaMalloc(&q, new_n * sizeof(T)));
+        CUDA_TRY(dev_alloc(&q, new_n * sizeof(T)));
         if (p && old_n) CUDA_TRY(cudaMemcpy(q, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice));
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = q;
         return NDP_OK;
     }
@@ -348,9 +369,9 @@ struct BfsLevelState {
             if ((rc = grow(nodes[b], node_cap, cap))) return rc;
             if ((rc = grow(node_tree[b], node_cap, cap))) return rc;
         }
-        if (children) cudaFree(children);
+        if (children) dev_free(children);
         children = nullptr;
-        CUDA_TRY(cudaMalloc(&children, cap * sizeof(BfsChild)));
+        CUDA_TRY(dev_alloc(&children, cap * sizeof(BfsChild)));
         node_cap = cap;
         return NDP_OK;
     }
@@ -372,10 +393,10 @@ struct BfsLevelState {
         return NDP_OK;
     }
     ~BfsLevelState() {
-        for (int b = 0; b < 2; ++b) { if (nodes[b]) cudaFree(nodes[b]); if (node_tree[b]) cudaFree(node_tree[b]); }
-        if (children) cudaFree(children);
-        if (tree_parent) cudaFree(tree_parent);
-        if (tree_lit) cudaFree(tree_lit);
+        for (int b = 0; b < 2; ++b) { if (nodes[b]) dev_free(nodes[b]); if (node_tree[b]) dev_free(node_tree[b]); }
+        if (children) dev_free(children);
+        if (tree_parent) dev_free(tree_parent);
+        if (tree_lit) dev_free(tree_lit);
         if (h_totals) cudaFreeHost((void*)h_totals);
     }
 };
@@ -399,8 +420,8 @@ int frontier_choices(ndp_frontier* f, size_t k, std::vector<int32_t>& out) {
     CUDA_TRY(cudaSetDevice(f->device));
     const int cap = std::max(f->max_var, 1) + 8;
     DevBuf d_out, d_len;
-    CUDA_TRY(cudaMalloc(&d_out.p, (size_t)cap * 4));
-    CUDA_TRY(cudaMalloc(&d_len.p, 4));
+    CUDA_TRY(dev_alloc(&d_out.p, (size_t)cap * 4));
+    CUDA_TRY(dev_alloc(&d_len.p, 4));
     tree_path_kernel<<<1, 1>>>(f->d_tree_parent, f->d_tree_lit, e.tree, d_out.as<int32_t>(), cap, d_len.as<int32_t>());
     CUDA_TRY(cudaGetLastError());
     int32_t len = 0;
@@ -429,7 +450,7 @@ int materialise(ndp_frontier* f, const std::vector<size_t>& which, pclause* d_ou
         ptrs[i] = f->sbuf[e.buf] + (size_t)e.slot * ix->slot_words;
     }
     DevBuf d_ptr;
-    CUDA_TRY(cudaMalloc(&d_ptr.p, std::max(ptrs.size(), (size_t)1) * sizeof(unsigned*)));
+    CUDA_TRY(dev_alloc(&d_ptr.p, std::max(ptrs.size(), (size_t)1) * sizeof(unsigned*)));
     CUDA_TRY(cudaMemcpy(d_ptr.p, ptrs.data(), ptrs.size() * sizeof(unsigned*), cudaMemcpyHostToDevice));
     const int wpb = 4;
     const int grid = (int)std::min<size_t>((which.size() + wpb - 1) / wpb, (size_t)148 * 16);
@@ -540,7 +561,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         if ((rc = ensure_arena(f->sbuf[0], f->scap_slots[0], 64, slot_bytes))) return rc;
         // root state = the bitmaps of the empty assignment
         DevBuf d_tab;
-        CUDA_TRY(cudaMalloc(&d_tab.p, std::max(ix->table_words, 1) * 4));
+        CUDA_TRY(dev_alloc(&d_tab.p, std::max(ix->table_words, 1) * 4));
         CUDA_TRY(cudaMemset(d_tab.p, 0, std::max(ix->table_words, 1) * 4));
         index_states_kernel<<<1, 32, ix->slot_words * 4>>>(*ix, d_tab.as<unsigned>(), f->sbuf[0], 1, st.nodes[0]);
         CUDA_TRY(cudaGetLastError());
@@ -583,19 +604,23 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     bool persist_ok = false, persist_rearm = false;
     size_t persist_cap = 0;
     DevBuf d_pstate;
-    int coop_grid = 0;
+    int coop_grid = 0, coop_warps = 0;
     if (use_index && !getenv("NDP_NO_PERSIST")) {
         int coop = 0, sms = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-        if (coop && 8 * slot_bytes <= 200 * 1024) {
+        // one CTA per SM, as many warps as state slots fit its shared memory (<= 32)
+        coop_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
+        if (const char* e = getenv("NDP_PERSIST_WARPS")) coop_warps = std::max(1, std::min(coop_warps, atoi(e)));
+        if (coop && coop_warps >= 4) {
             CUDA_TRY(cudaFuncSetAttribute(bfs_index_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(8 * slot_bytes)));
+                                          (int)(coop_warps * slot_bytes)));
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_index_persistent_kernel, 256, 8 * slot_bytes));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_index_persistent_kernel, coop_warps * 32,
+                                                                   coop_warps * slot_bytes));
             if (per_sm >= 1) {
-                coop_grid = sms * std::min(per_sm, 2);
-                CUDA_TRY(cudaMalloc(&d_pstate.p, sizeof(PersistState)));
+                coop_grid = sms;
+                CUDA_TRY(dev_alloc(&d_pstate.p, sizeof(PersistState)));
                 persist_ok = true;
                 const size_t budget = ((size_t)4 << 30) / slot_bytes;   // <= 4 GB per buffer up front
                 persist_cap = Q > 0 ? std::min<size_t>(2 * (size_t)Q, budget) : std::min<size_t>(8192, budget);
@@ -686,8 +711,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 int Dv = D, Qv = Q, ovrv = ovr ? 1 : 0, maxl = 1 << 20;
                 PersistState* dps = d_pstate.as<PersistState>();
                 void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps};
-                cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid), dim3(256),
-                                                             args, 8 * slot_bytes, 0);
+                cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid),
+                                                             dim3(coop_warps * 32), args, coop_warps * slot_bytes, 0);
                 if (le == cudaSuccess) le = cudaStreamSynchronize(0);
                 if (le != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS persistent kernel: ") + cudaGetErrorString(le)); break; }
                 CUDA_TRY(cudaMemcpy(&ps, d_pstate.p, sizeof ps, cudaMemcpyDeviceToHost));
@@ -898,7 +923,7 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
         if (f->states && !f->materialised) {
             // one element: filter the root by this node's assignment into a scratch slot
             const size_t cap = (size_t)pad_up((int)(f->root_c3.size() / 3) + 1);
-            if (!f->d_get) CUDA_TRY(cudaMalloc(&f->d_get, cap * sizeof(pclause)));
+            if (!f->d_get) CUDA_TRY(dev_alloc(&f->d_get, cap * sizeof(pclause)));
             int rc = materialise(f, std::vector<size_t>{k}, f->d_get, cap);
             if (rc) return rc;
             src = f->d_get;
@@ -1041,7 +1066,7 @@ int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_
     std::vector<int32_t> h_n(std::max(r.n_local, (size_t)1));
     if (device != f->device && r.n_local) {
         // private copy of this shard's slots on the other GPU, one peer copy per slot
-        CUDA_TRY(cudaMalloc(&r.shard_buf, r.n_local * f->stride * sizeof(pclause)));
+        CUDA_TRY(dev_alloc(&r.shard_buf, r.n_local * f->stride * sizeof(pclause)));
         for (size_t q = 0; q < r.n_local; ++q) {
             const size_t k = first + q * stride;
             CUDA_TRY(cudaMemcpyPeerAsync(r.shard_buf + q * f->stride, device, clause_slot(f, k), f->device,
@@ -1055,8 +1080,8 @@ int build_replica(ndp_frontier* f, int device, size_t first, size_t stride, ndp_
         h_n[q] = f->entries[k].n;
         r.n_max = std::max(r.n_max, f->entries[k].n);
     }
-    CUDA_TRY(cudaMalloc((void**)&r.d_base, h_base.size() * sizeof(pclause*)));
-    CUDA_TRY(cudaMalloc(&r.d_n, h_n.size() * sizeof(int32_t)));
+    CUDA_TRY(dev_alloc((void**)&r.d_base, h_base.size() * sizeof(pclause*)));
+    CUDA_TRY(dev_alloc(&r.d_n, h_n.size() * sizeof(int32_t)));
     CUDA_TRY(cudaMemcpy((void*)r.d_base, h_base.data(), h_base.size() * sizeof(pclause*), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r.d_n, h_n.data(), h_n.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     f->replicas.push_back(r);
@@ -1122,14 +1147,14 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
     r.n_local = first < total ? (total - first + stride - 1) / stride : 0;
     const size_t nl1 = std::max(r.n_local, (size_t)1);
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMalloc((void**)&r.d_slot_ptr, nl1 * sizeof(unsigned*)));
-    CUDA_TRY(cudaMalloc(&r.d_meta, nl1 * sizeof(BfsNode)));
+    CUDA_TRY(dev_alloc((void**)&r.d_slot_ptr, nl1 * sizeof(unsigned*)));
+    CUDA_TRY(dev_alloc(&r.d_meta, nl1 * sizeof(BfsNode)));
     std::vector<const unsigned*> h_ptr(nl1, nullptr);
     std::vector<BfsNode> h_meta(nl1);
     if (f->states) {
         // the BFS already produced state slots: use them in place (home device) or copy the shard over
         if (device != f->device && r.n_local) {
-            CUDA_TRY(cudaMalloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
+            CUDA_TRY(dev_alloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
             for (size_t q = 0; q < r.n_local; ++q) {
                 const Entry& e = f->entries[first + q * stride];
                 CUDA_TRY(cudaMemcpyPeerAsync(r.own_slots + q * ix.slot_words, device,
@@ -1149,11 +1174,11 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
         // tree on the device) -> state slot
         DevBuf d_tables, d_entry, d_tp, d_tl;
         const size_t tbytes = r.n_local * (size_t)ix.table_words * 4;
-        CUDA_TRY(cudaMalloc(&d_tables.p, std::max(tbytes, (size_t)4)));
+        CUDA_TRY(dev_alloc(&d_tables.p, std::max(tbytes, (size_t)4)));
         CUDA_TRY(cudaMemset(d_tables.p, 0, std::max(tbytes, (size_t)4)));
         std::vector<int32_t> h_entry_tree(total);
         for (size_t k = 0; k < total; ++k) h_entry_tree[k] = f->entries[k].tree;
-        CUDA_TRY(cudaMalloc(&d_entry.p, total * 4));
+        CUDA_TRY(dev_alloc(&d_entry.p, total * 4));
         CUDA_TRY(cudaMemcpy(d_entry.p, h_entry_tree.data(), total * 4, cudaMemcpyHostToDevice));
         f->h2d_bytes += total * 4;
         const int32_t *tp = f->d_tree_parent, *tl = f->d_tree_lit;
@@ -1161,8 +1186,8 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
             if ((rc = ensure_host_tree(f))) return rc;
             CUDA_TRY(cudaSetDevice(device));
             const size_t tn = f->tree_parent.size();
-            CUDA_TRY(cudaMalloc(&d_tp.p, tn * 4));
-            CUDA_TRY(cudaMalloc(&d_tl.p, tn * 4));
+            CUDA_TRY(dev_alloc(&d_tp.p, tn * 4));
+            CUDA_TRY(dev_alloc(&d_tl.p, tn * 4));
             CUDA_TRY(cudaMemcpy(d_tp.p, f->tree_parent.data(), tn * 4, cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(d_tl.p, f->tree_lit.data(), tn * 4, cudaMemcpyHostToDevice));
             f->h2d_bytes += tn * 8;
@@ -1174,7 +1199,7 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
         prefix_table_kernel<<<blocks, threads>>>(d_entry.as<int32_t>(), tp, tl, first, stride, r.n_local,
                                                  ix.table_words, d_tables.as<unsigned>());
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMalloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
+        CUDA_TRY(dev_alloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
         const int wpb = 4;
         const int grid = (int)std::min<size_t>((r.n_local + wpb - 1) / wpb, (size_t)148 * 16);
         index_states_kernel<<<grid, wpb * 32, wpb * ix.slot_words * 4>>>(ix, d_tables.as<unsigned>(), r.own_slots,
@@ -1224,19 +1249,19 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     }
 
     DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_msub, b_mlen, b_models, b_scratch;
-    CUDA_TRY(cudaMalloc(&b_verdict.p, nl));
-    CUDA_TRY(cudaMalloc(&b_nodes.p, nl * 8));
-    CUDA_TRY(cudaMalloc(&b_evals.p, nl * 8));
-    CUDA_TRY(cudaMalloc(&b_reb.p, nl * 4));
-    CUDA_TRY(cudaMalloc(&b_next.p, 4));
-    CUDA_TRY(cudaMalloc(&b_msub.p, (size_t)n_warps * 8));
-    CUDA_TRY(cudaMalloc(&b_mlen.p, (size_t)n_warps * 4));
-    CUDA_TRY(cudaMalloc(&b_models.p, (size_t)n_warps * model_stride * 4));
-    if (use_index) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
-    else if (!plan.smem_w) CUDA_TRY(cudaMalloc(&b_scratch.p, (size_t)n_warps * plan.p.w_cap * sizeof(pclause)));
+    CUDA_TRY(dev_alloc(&b_verdict.p, nl));
+    CUDA_TRY(dev_alloc(&b_nodes.p, nl * 8));
+    CUDA_TRY(dev_alloc(&b_evals.p, nl * 8));
+    CUDA_TRY(dev_alloc(&b_reb.p, nl * 4));
+    CUDA_TRY(dev_alloc(&b_next.p, 4));
+    CUDA_TRY(dev_alloc(&b_msub.p, (size_t)n_warps * 8));
+    CUDA_TRY(dev_alloc(&b_mlen.p, (size_t)n_warps * 4));
+    CUDA_TRY(dev_alloc(&b_models.p, (size_t)n_warps * model_stride * 4));
+    if (use_index) CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
+    else if (!plan.smem_w) CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * plan.p.w_cap * sizeof(pclause)));
     unsigned long long* d_best = shared_best;
     if (!d_best) {
-        CUDA_TRY(cudaMalloc(&b_best.p, 8));
+        CUDA_TRY(dev_alloc(&b_best.p, 8));
         d_best = b_best.as<unsigned long long>();
         CUDA_TRY(cudaMemcpy(d_best, &best_init, 8, cudaMemcpyHostToDevice));
     }

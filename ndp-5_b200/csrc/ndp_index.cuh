@@ -338,7 +338,7 @@ struct PersistState {
     unsigned long long cap_slots, cap_nodes, cap_tree;
 };
 
-__global__ void __launch_bounds__(256) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
+__global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
                                                                    BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
                                                                    int32_t* ntree1, BfsChild* children,
                                                                    int32_t* tree_parent, int32_t* tree_lit, int D, int Q,
@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(256) bfs_index_persistent_kernel(const IndexRo
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned smem_words[];
-    __shared__ unsigned warp_count[8];
-    __shared__ unsigned long long red_evals[8];
-    __shared__ unsigned red_exp[8];
+    __shared__ unsigned warp_count[32];
+    __shared__ unsigned long long red_evals[32];
+    __shared__ unsigned red_exp[32];
     __shared__ unsigned stop_flag, s_running;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int warps_per_block = blockDim.x >> 5;
