@@ -61,6 +61,15 @@ int ndp_device_count(int* count);
  * overrides AUTO. */
 enum { NDP_ENGINE_AUTO = 0, NDP_ENGINE_SCAN = 1, NDP_ENGINE_INDEX = 2 };
 int ndp_set_engine(int engine);
+/* DFS work decomposition (index engine).  The reference's Satisfy_iterative is sequential inside
+ * one subproblem (NDP:784-878) and a frontier can be narrower than the device (-d 12 yields ONE
+ * subproblem: NDP:926,935).  A shard with fewer subproblems than the GPU has warps is therefore
+ * first cut into PIECES -- subtrees of each subproblem's search tree, listed in the order the
+ * reference's LIFO stack reaches them -- and the pieces are searched in parallel.  Results are
+ * unchanged: same verdict per subproblem, the same (first-in-DFS-order) model, the same node and
+ * clause-evaluation counts.  pieces = -1: automatic (default), 0: never split, > 0: split every
+ * shard with fewer subproblems into about that many pieces.  Env NDP_SPLIT=<n>|off overrides -1. */
+int ndp_set_split(long long pieces);
 const char* ndp_last_error(void);
 const char* ndp_version(void);
 

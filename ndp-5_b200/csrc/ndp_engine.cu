@@ -8,6 +8,7 @@
 #include "../../include/ndp_b200.h"
 #include "ndp_kernels.cuh"
 #include "ndp_index.cuh"
+#include "ndp_split.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -29,6 +30,7 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_device = 0;
 int g_engine = NDP_ENGINE_AUTO;   // process-wide; ndp_set_engine / env NDP_ENGINE
+long long g_split = -1;           // process-wide; ndp_set_split / env NDP_SPLIT (-1 auto, 0 off, > 0 piece target)
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -499,6 +501,11 @@ int ndp_set_engine(int engine) {
     if (engine != NDP_ENGINE_AUTO && engine != NDP_ENGINE_SCAN && engine != NDP_ENGINE_INDEX)
         return fail(NDP_E_INVALID, "unknown engine");
     g_engine = engine;
+    return NDP_OK;
+}
+int ndp_set_split(long long pieces) {
+    if (pieces < -1) return fail(NDP_E_INVALID, "split target must be -1 (auto), 0 (off) or a piece count");
+    g_split = pieces;
     return NDP_OK;
 }
 int ndp_device_count(int* count) {
@@ -1215,6 +1222,115 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
     return NDP_OK;
 }
 
+// ---- DFS-order split of a narrow shard (ndp_split.cuh) ----------------------------------------
+struct SplitRun {
+    bool active = false;
+    DevBuf ptr[2], meta[2], orig[2], tnode[2], pre_n[2], pre_e[2], sbuf[2];
+    DevBuf children, parents, t_parent, t_lit, t_off, t_len, log, tail_n, tail_e, state;
+    SplitParams sp;
+    SplitState st;
+    size_t n_pieces = 0;
+    int side = 0;       // which SplitLevel holds the final pieces
+};
+
+// How many pieces the shard should be cut into (0 = leave the subproblems whole).
+size_t split_target(size_t n_sub, int n_warps) {
+    long long mode = g_split;
+    if (mode < 0)
+        if (const char* e = getenv("NDP_SPLIT")) mode = !strcmp(e, "off") ? 0 : atoll(e);
+    if (mode == 0 || n_sub == 0) return 0;
+    if (mode > 0) return (size_t)mode > n_sub ? (size_t)mode : 0;
+    // auto: only shards that cannot occupy the device (fewer than two subproblems per resident warp)
+    return n_sub < (size_t)2 * n_warps ? (size_t)4 * n_warps : 0;
+}
+
+int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
+              ndp_stats* stats) {
+    const size_t n_sub = rep.n_local;
+    int sms = 0, coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    SplitParams& sp = run.sp;
+    sp.ix = ix;
+    sp.chain_cap = 128;
+    sp.max_levels = 64;
+    if (const char* e = getenv("NDP_SPLIT_CHAIN")) sp.chain_cap = std::max(1, std::min(4096, atoi(e)));
+    if (const char* e = getenv("NDP_SPLIT_LEVELS")) sp.max_levels = std::max(1, atoi(e));
+    sp.target = (unsigned)std::min<size_t>(target, 1u << 22);
+    sp.off_chain = (int)align16((size_t)ix.slot_words * 4);
+    sp.warp_bytes = sp.off_chain + (int)align16((size_t)sp.chain_cap * 2);
+    const int warps = (int)std::min<size_t>(32, ((size_t)200 * 1024) / (size_t)sp.warp_bytes);
+    if (!coop || warps < 1) return NDP_OK;   // cannot co-schedule the grid: search the subproblems whole
+    CUDA_TRY(cudaFuncSetAttribute(dfs_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * sp.warp_bytes));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfs_split_kernel, warps * 32,
+                                                           (size_t)warps * sp.warp_bytes));
+    if (per_sm < 1) return NDP_OK;
+    const size_t cap = 2 * (size_t)sp.target;                 // pieces per level (children of a level: <= cap)
+    const size_t cap_tree = n_sub + 24 * cap;
+    const size_t cap_log = std::max<size_t>((size_t)16 << 20, 4 * cap * (size_t)sp.chain_cap / 8);
+    const size_t slot_bytes = (size_t)ix.slot_words * 4;
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(dev_alloc(&run.ptr[b].p, cap * sizeof(unsigned*)));
+        CUDA_TRY(dev_alloc(&run.meta[b].p, cap * sizeof(BfsNode)));
+        CUDA_TRY(dev_alloc(&run.orig[b].p, cap * 4));
+        CUDA_TRY(dev_alloc(&run.tnode[b].p, cap * 4));
+        CUDA_TRY(dev_alloc(&run.pre_n[b].p, cap * 8));
+        CUDA_TRY(dev_alloc(&run.pre_e[b].p, cap * 8));
+        CUDA_TRY(dev_alloc(&run.sbuf[b].p, cap * slot_bytes));
+        sp.lv[b].ptr = run.ptr[b].as<const unsigned*>();
+        sp.lv[b].meta = run.meta[b].as<BfsNode>();
+        sp.lv[b].orig = run.orig[b].as<int32_t>();
+        sp.lv[b].tnode = run.tnode[b].as<int32_t>();
+        sp.lv[b].pre_nodes = run.pre_n[b].as<unsigned long long>();
+        sp.lv[b].pre_evals = run.pre_e[b].as<unsigned long long>();
+        sp.sbuf[b] = run.sbuf[b].as<unsigned>();
+    }
+    CUDA_TRY(dev_alloc(&run.children.p, cap * sizeof(BfsChild)));
+    CUDA_TRY(dev_alloc(&run.parents.p, (cap / 2 + 1) * sizeof(SplitParent)));
+    CUDA_TRY(dev_alloc(&run.t_parent.p, cap_tree * 4));
+    CUDA_TRY(dev_alloc(&run.t_lit.p, cap_tree * 4));
+    CUDA_TRY(dev_alloc(&run.t_off.p, cap_tree * 4));
+    CUDA_TRY(dev_alloc(&run.t_len.p, cap_tree * 4));
+    CUDA_TRY(dev_alloc(&run.log.p, cap_log * sizeof(short)));
+    CUDA_TRY(dev_alloc(&run.tail_n.p, n_sub * 8));
+    CUDA_TRY(dev_alloc(&run.tail_e.p, n_sub * 8));
+    CUDA_TRY(dev_alloc(&run.state.p, sizeof(SplitState)));
+    sp.children = run.children.as<BfsChild>();
+    sp.parents = run.parents.as<SplitParent>();
+    sp.t_parent = run.t_parent.as<int32_t>();
+    sp.t_lit = run.t_lit.as<int32_t>();
+    sp.t_seg_off = run.t_off.as<unsigned>();
+    sp.t_seg_len = run.t_len.as<unsigned>();
+    sp.log = run.log.as<short>();
+    sp.tail_nodes = run.tail_n.as<unsigned long long>();
+    sp.tail_evals = run.tail_e.as<unsigned long long>();
+    sp.st = run.state.as<SplitState>();
+    SplitState& st = run.st;
+    memset(&st, 0, sizeof st);
+    st.m = (int)n_sub;
+    st.tree_count = n_sub;
+    st.cap_pieces = cap;
+    st.cap_tree = cap_tree;
+    st.cap_log = cap_log;
+    CUDA_TRY(cudaMemcpyAsync(sp.st, &st, sizeof st, cudaMemcpyHostToDevice, 0));
+    split_init_kernel<<<(int)std::min<size_t>((n_sub + 255) / 256, 1024), 256>>>(sp, rep.d_slot_ptr, rep.d_meta, (int)n_sub);
+    CUDA_TRY(cudaGetLastError());
+    void* args[] = {&sp};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dfs_split_kernel, dim3(sms), dim3(warps * 32), args,
+                                         (size_t)warps * sp.warp_bytes, 0));
+    CUDA_TRY(cudaMemcpy(&st, sp.st, sizeof st, cudaMemcpyDeviceToHost));
+    run.active = true;
+    run.n_pieces = (size_t)st.m;
+    run.side = st.cur;
+    if (stats) { stats->launches += 2; stats->h2d_bytes += sizeof st; stats->d2h_bytes += sizeof st; }
+    if (tracing())
+        fprintf(stderr, "[ndp_split] %zu subproblems -> %zu pieces in %d levels (exit %d), tree %llu, log %llu\n", n_sub,
+                run.n_pieces, st.levels_done, st.exit_reason, st.tree_count, st.log_count);
+    return NDP_OK;
+}
+
 // One shard on one device.  `shared_best`/`peer_best`: early-exit words (this device's + peers').
 int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int early_exit,
                   unsigned long long* shared_best, unsigned long long* const* peer_best, int n_peers,
@@ -1229,10 +1345,10 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     else rc = build_replica(f, device, first, stride, &rep);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
-    const size_t nl = use_index ? irep->n_local : rep->n_local;
+    const size_t n_sub = use_index ? irep->n_local : rep->n_local;   // subproblems of this shard
     if (winner) *winner = SIZE_MAX;
-    if (nl == 0) return NDP_OK;
-    if (nl > 0xfffffff0ull) return fail(NDP_E_UNSUPPORTED, "shard larger than the 32-bit work counter");
+    if (n_sub == 0) return NDP_OK;
+    if (n_sub > 0x7ffffff0ull) return fail(NDP_E_UNSUPPORTED, "shard larger than the 32-bit work counter");
 
     DfsLaunchPlan plan;
     IndexLaunchPlan iplan;
@@ -1248,34 +1364,62 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         model_stride = plan.p.model_stride;
     }
 
-    DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_msub, b_mlen, b_models, b_scratch;
-    CUDA_TRY(dev_alloc(&b_verdict.p, nl));
-    CUDA_TRY(dev_alloc(&b_nodes.p, nl * 8));
-    CUDA_TRY(dev_alloc(&b_evals.p, nl * 8));
-    CUDA_TRY(dev_alloc(&b_reb.p, nl * 4));
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    struct EvFree { cudaEvent_t a, b; ~EvFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_free{ev0, ev1};
+    CUDA_TRY(cudaEventRecord(ev0, 0));
+
+    // index engine: a shard too narrow for the device is first cut into pieces in DFS order
+    SplitRun split;
+    if (use_index) {
+        const size_t target = split_target(n_sub, n_warps);
+        if (target > n_sub && (rc = run_split(device, *ix, *irep, target, split, stats))) return rc;
+    }
+    const size_t nl = split.active ? split.n_pieces : n_sub;         // units the DFS kernel pulls
+
+    DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_bestp, b_msub, b_mlen, b_models, b_scratch;
+    const size_t nl1 = std::max(nl, (size_t)1);
+    CUDA_TRY(dev_alloc(&b_verdict.p, nl1));
+    CUDA_TRY(dev_alloc(&b_nodes.p, nl1 * 8));
+    CUDA_TRY(dev_alloc(&b_evals.p, nl1 * 8));
+    CUDA_TRY(dev_alloc(&b_reb.p, nl1 * 4));
     CUDA_TRY(dev_alloc(&b_next.p, 4));
     CUDA_TRY(dev_alloc(&b_msub.p, (size_t)n_warps * 8));
     CUDA_TRY(dev_alloc(&b_mlen.p, (size_t)n_warps * 4));
     CUDA_TRY(dev_alloc(&b_models.p, (size_t)n_warps * model_stride * 4));
-    if (use_index) CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
-    else if (!plan.smem_w) CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * plan.p.w_cap * sizeof(pclause)));
+    if (use_index) {
+        CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
+        CUDA_TRY(dev_alloc(&b_bestp.p, n_sub * 4));
+        CUDA_TRY(cudaMemsetAsync(b_bestp.p, 0xff, n_sub * 4, 0));
+    } else if (!plan.smem_w) {
+        CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * plan.p.w_cap * sizeof(pclause)));
+    }
     unsigned long long* d_best = shared_best;
     if (!d_best) {
         CUDA_TRY(dev_alloc(&b_best.p, 8));
         d_best = b_best.as<unsigned long long>();
-        CUDA_TRY(cudaMemcpy(d_best, &best_init, 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(d_best, &best_init, 8, cudaMemcpyHostToDevice, 0));
     }
-    CUDA_TRY(cudaMemset(b_verdict.p, NDP_NOT_RUN, nl));
-    CUDA_TRY(cudaMemset(b_next.p, 0, 4));
-    CUDA_TRY(cudaMemset(b_msub.p, 0xff, (size_t)n_warps * 8));
+    CUDA_TRY(cudaMemsetAsync(b_verdict.p, NDP_NOT_RUN, nl1, 0));
+    CUDA_TRY(cudaMemsetAsync(b_next.p, 0, 4, 0));
+    CUDA_TRY(cudaMemsetAsync(b_msub.p, 0xff, (size_t)n_warps * 8, 0));
 
-    cudaEvent_t ev0, ev1;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
-    if (use_index) {
+    if (nl == 0) {
+        // every piece died inside the split: nothing left to search
+    } else if (use_index) {
         IndexParams& p = iplan.p;
-        p.slot_ptr = irep->d_slot_ptr;
-        p.meta = irep->d_meta;
+        if (split.active) {
+            const SplitLevel& L = split.sp.lv[split.side];
+            p.slot_ptr = L.ptr;
+            p.meta = L.meta;
+            p.orig = L.orig;
+        } else {
+            p.slot_ptr = irep->d_slot_ptr;
+            p.meta = irep->d_meta;
+            p.orig = nullptr;
+        }
+        p.best_piece = b_bestp.as<unsigned int>();
         p.first = first; p.stride = stride; p.n_local = nl;
         p.next = b_next.as<unsigned int>();
         p.best = d_best;
@@ -1298,7 +1442,6 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
             int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
             cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
-        CUDA_TRY(cudaEventRecord(ev0, 0));
         dfs_index_kernel<<<iplan.grid, iplan.warps_per_cta * 32, iplan.smem_bytes>>>(p);
     } else {
         DfsParams& p = plan.p;
@@ -1321,7 +1464,6 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.gscratch = b_scratch.as<pclause>();
         auto kern = plan.smem_w ? dfs_kernel<true> : dfs_kernel<false>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-        CUDA_TRY(cudaEventRecord(ev0, 0));
         kern<<<plan.grid, plan.warps_per_cta * 32, plan.smem_bytes>>>(p);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1329,51 +1471,123 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(cudaEventSynchronize(ev1));
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
 
-    std::vector<uint8_t> h_v(nl);
-    std::vector<unsigned long long> h_nodes(nl), h_evals(nl);
-    std::vector<unsigned> h_reb(nl);
-    CUDA_TRY(cudaMemcpy(h_v.data(), b_verdict.p, nl, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h_nodes.data(), b_nodes.p, nl * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h_evals.data(), b_evals.p, nl * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h_reb.data(), b_reb.p, nl * 4, cudaMemcpyDeviceToHost));
-    size_t win = SIZE_MAX;
-    uint64_t tn = 0, te = 0, tr = 0;
-    for (size_t q = 0; q < nl; ++q) {
+    // ---- per-piece results -> per-subproblem results
+    std::vector<uint8_t> h_v(nl1);
+    std::vector<unsigned long long> h_nodes(nl1), h_evals(nl1);
+    std::vector<unsigned> h_reb(nl1);
+    size_t d2h = 0;
+    if (nl) {
+        CUDA_TRY(cudaMemcpy(h_v.data(), b_verdict.p, nl, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_nodes.data(), b_nodes.p, nl * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_evals.data(), b_evals.p, nl * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_reb.data(), b_reb.p, nl * 4, cudaMemcpyDeviceToHost));
+        d2h += nl * (1 + 8 + 8 + 4);
+    }
+    std::vector<uint8_t> sub_v;
+    std::vector<unsigned long long> sub_nodes, sub_evals;
+    std::vector<unsigned> h_bestp;
+    uint64_t tr = 0;
+    for (size_t q = 0; q < nl; ++q) tr += h_reb[q];
+    if (split.active) {
+        std::vector<int32_t> h_orig(nl1);
+        std::vector<unsigned long long> h_pre_n(nl1), h_pre_e(nl1), h_tail_n(n_sub), h_tail_e(n_sub);
+        h_bestp.resize(n_sub);
+        const SplitLevel& L = split.sp.lv[split.side];
+        if (nl) {
+            CUDA_TRY(cudaMemcpy(h_orig.data(), L.orig, nl * 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h_pre_n.data(), L.pre_nodes, nl * 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h_pre_e.data(), L.pre_evals, nl * 8, cudaMemcpyDeviceToHost));
+        }
+        CUDA_TRY(cudaMemcpy(h_tail_n.data(), split.sp.tail_nodes, n_sub * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_tail_e.data(), split.sp.tail_evals, n_sub * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_bestp.data(), b_bestp.p, n_sub * 4, cudaMemcpyDeviceToHost));
+        d2h += nl * 20 + n_sub * 20;
+        sub_v.assign(n_sub, NDP_UNSAT);
+        sub_nodes.assign(n_sub, 0);
+        sub_evals.assign(n_sub, 0);
+        // nodes(subproblem) = pieces up to and including the first one with a model, each with the
+        // interior nodes charged to it; an UNSAT subproblem adds the dead ends after its last piece
+        for (size_t pc = 0; pc < nl; ++pc) {
+            const size_t o = (size_t)h_orig[pc];
+            const unsigned w = h_bestp[o];
+            if (w != 0xffffffffu && pc > (size_t)w) continue;
+            sub_nodes[o] += h_pre_n[pc] + h_nodes[pc];
+            sub_evals[o] += h_pre_e[pc] + h_evals[pc];
+            if (h_v[pc] == NDP_NOT_RUN && sub_v[o] == NDP_UNSAT) sub_v[o] = NDP_NOT_RUN;
+        }
+        for (size_t o = 0; o < n_sub; ++o) {
+            if (h_bestp[o] != 0xffffffffu) sub_v[o] = NDP_SAT;
+            else if (sub_v[o] == NDP_UNSAT) { sub_nodes[o] += h_tail_n[o]; sub_evals[o] += h_tail_e[o]; }
+        }
+    } else {
+        sub_v.swap(h_v);
+        sub_nodes.swap(h_nodes);
+        sub_evals.swap(h_evals);
+    }
+    size_t win = SIZE_MAX, win_q = SIZE_MAX;
+    uint64_t tn = 0, te = 0;
+    for (size_t q = 0; q < n_sub; ++q) {
         const size_t g = first + q * stride;
-        if (verdict) verdict[g] = h_v[q];
-        if (nodes) nodes[g] = h_nodes[q];
-        if (evals) evals[g] = h_evals[q];
-        tn += h_nodes[q]; te += h_evals[q]; tr += h_reb[q];
-        if (h_v[q] == NDP_SAT && win == SIZE_MAX) win = g;
+        if (verdict) verdict[g] = sub_v[q];
+        if (nodes) nodes[g] = sub_nodes[q];
+        if (evals) evals[g] = sub_evals[q];
+        tn += sub_nodes[q]; te += sub_evals[q];
+        if (sub_v[q] == NDP_SAT && win == SIZE_MAX) { win = g; win_q = q; }
     }
     if (winner) *winner = win;
     if (win != SIZE_MAX && model) {
+        // the piece (= the subproblem itself without a split) whose model is the reference's
+        const unsigned long long win_piece = split.active ? (unsigned long long)h_bestp[win_q]
+                                             : (use_index ? (unsigned long long)win_q : (unsigned long long)win);
         std::vector<unsigned long long> h_msub(n_warps);
         std::vector<int32_t> h_mlen(n_warps);
         CUDA_TRY(cudaMemcpy(h_msub.data(), b_msub.p, (size_t)n_warps * 8, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(h_mlen.data(), b_mlen.p, (size_t)n_warps * 4, cudaMemcpyDeviceToHost));
+        d2h += (size_t)n_warps * 12;
         model->clear();
-        for (int w = 0; w < n_warps; ++w)
-            if (h_msub[w] == (unsigned long long)win) {
+        bool found = false;
+        for (int w = 0; w < n_warps && !found; ++w)
+            if (h_msub[w] == win_piece) {
+                found = true;
                 if ((rc = frontier_choices(f, win, *model))) return rc;   // choices_k ++ dfs choices (NDP:1430-1431)
+                if (split.active) {
+                    // ... ++ the choices the split made on the way to the winning piece
+                    const int cap = std::max(f->max_var, 1) + 8;
+                    int32_t leaf = -1, start = 0;
+                    CUDA_TRY(cudaMemcpy(&leaf, split.sp.lv[split.side].tnode + win_piece, 4, cudaMemcpyDeviceToHost));
+                    DevBuf d_out, d_start;
+                    CUDA_TRY(dev_alloc(&d_out.p, (size_t)cap * 4));
+                    CUDA_TRY(dev_alloc(&d_start.p, 4));
+                    split_path_kernel<<<1, 1>>>(split.sp.t_parent, split.sp.t_lit, split.sp.t_seg_off, split.sp.t_seg_len,
+                                                split.sp.log, leaf, d_out.as<int32_t>(), cap, d_start.as<int32_t>());
+                    CUDA_TRY(cudaGetLastError());
+                    CUDA_TRY(cudaMemcpy(&start, d_start.p, 4, cudaMemcpyDeviceToHost));
+                    if (start < 0) return fail(NDP_E_CUDA, "split path longer than the variable count");
+                    std::vector<int32_t> path((size_t)(cap - start));
+                    if (!path.empty())
+                        CUDA_TRY(cudaMemcpy(path.data(), d_out.as<int32_t>() + start, path.size() * 4, cudaMemcpyDeviceToHost));
+                    model->insert(model->end(), path.begin(), path.end());
+                    d2h += 8 + path.size() * 4;
+                    if (stats) stats->launches += 1;
+                }
                 std::vector<int32_t> tail((size_t)h_mlen[w]);
-                CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * model_stride,
-                                    tail.size() * 4, cudaMemcpyDeviceToHost));
+                if (!tail.empty())
+                    CUDA_TRY(cudaMemcpy(tail.data(), b_models.as<int32_t>() + (size_t)w * model_stride,
+                                        tail.size() * 4, cudaMemcpyDeviceToHost));
                 model->insert(model->end(), tail.begin(), tail.end());
-                break;
+                d2h += tail.size() * 4;
             }
+        if (!found) return fail(NDP_E_CUDA, "the winning piece's model was not parked");
     }
     if (stats) {
         stats->h2d_bytes += 8 + 4;                                   // early-exit word + work counter
-        stats->d2h_bytes += nl * (1 + 8 + 8 + 4) + (win != SIZE_MAX && model ? (size_t)n_warps * 12 + model->size() * 4 : 0);
+        stats->d2h_bytes += d2h;
         stats->nodes += tn;
         stats->clause_evals += te;
         stats->rebuilds += tr;
         stats->kernel_ms = std::max(stats->kernel_ms, (double)ms);
-        stats->launches += 1;
+        stats->launches += nl ? 1 : 0;
     }
     return NDP_OK;
 }

@@ -531,12 +531,21 @@ __global__ void __launch_bounds__(128) index_materialise_kernel(const IndexRoot 
 // state slot into shared memory and runs the whole search there.  The explicit stack is the trail
 // (global memory) plus one pending bit per trail position; a popped LA sibling is re-derived from
 // (slot table + trail) with one pass over the root.
+// The unit of work is a PIECE: a whole subproblem of the shard (orig == nullptr: piece q is
+// subproblem q), or -- after the DFS-order split of ndp_split.cuh -- a subtree of one, listed in
+// the order Satisfy_iterative would reach it.  best_piece[o] is the lowest piece of subproblem o
+// that holds a model: later pieces of o are abandoned, because the reference stops a subproblem
+// at its first model (NDP:823,849,869).
+constexpr int K_LEAF = 3;   // piece kind: a branch the split found empty -- the model itself, no node left to visit
+
 struct IndexParams {
     IndexRoot ix;
-    const unsigned* const* slot_ptr;  // [n_local] state slot of each subproblem
-    const BfsNode* meta;              // [n_local] n / kind / lit of each subproblem
+    const unsigned* const* slot_ptr;  // [n_local] state slot of each piece
+    const BfsNode* meta;              // [n_local] n / kind / lit of each piece
+    const int32_t* orig;              // [n_local] subproblem (local index) a piece belongs to, or nullptr = identity
+    unsigned int* best_piece;         // [subproblems of the shard] lowest piece with a model (0xffffffff: none)
     int pend_words, trail_cap;
-    unsigned long long first, stride, n_local;
+    unsigned long long first, stride, n_local;   // n_local = pieces
     unsigned int* next;
     unsigned long long* best;
     unsigned long long* peer_best[8];
@@ -546,7 +555,7 @@ struct IndexParams {
     unsigned long long* nodes;
     unsigned long long* evals;
     unsigned int* rebuilds;
-    unsigned long long* model_sub;    // [n_warps]
+    unsigned long long* model_sub;    // [n_warps] PIECE whose model the warp parked
     int32_t* model_len;               // [n_warps]
     short* trails;                    // [n_warps][trail_cap] working trail of each warp
     int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
@@ -570,25 +579,31 @@ __global__ void dfs_index_kernel(const IndexParams p) {
         if (lane == 0) q = atomicAdd(p.next, 1u);
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= p.n_local) break;
-        const unsigned long long g = p.first + (unsigned long long)q * p.stride;
-        if (p.early_exit && *(volatile unsigned long long*)p.best < g) {
+        const unsigned o = p.orig ? (unsigned)p.orig[q] : q;
+        const unsigned long long g = p.first + (unsigned long long)o * p.stride;
+        volatile unsigned int* my_best = p.best_piece + o;
+        if ((p.early_exit && *(volatile unsigned long long*)p.best < g) || *my_best < q) {
             if (lane == 0) { p.verdict[q] = 2; p.nodes[q] = 0; p.evals[q] = 0; p.rebuilds[q] = 0; }
             continue;
         }
         const unsigned* slot = p.slot_ptr[q];
-        __syncwarp();
-        slot_copy(B, slot, ix.slot_words, lane);
-        for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
         const BfsNode nd = p.meta[q];
         int n_live = nd.n, kind = nd.kind, lit = nd.lit;
-        __syncwarp();
         int ntrail = 0;
         unsigned long long nodes = 0, evals = 0;
         unsigned rebuilds = 0;
         int verdict = 0;
-        for (;;) {
+        __syncwarp();
+        if (kind != K_LEAF) {
+            slot_copy(B, slot, ix.slot_words, lane);
+            for (int w = lane; w < p.pend_words; w += 32) pend[w] = 0u;
+        }
+        __syncwarp();
+        if (kind == K_LEAF) verdict = 1;   // the split already reached the model: no node left to visit
+        else for (;;) {
             ++nodes;  // one Satisfy_iterative loop iteration (NDP:801-806)
-            if (p.early_exit && (nodes & 63u) == 0 && *(volatile unsigned long long*)p.best < g) { verdict = 2; break; }
+            if ((nodes & 63u) == 0 &&
+                ((p.early_exit && *(volatile unsigned long long*)p.best < g) || *my_best < q)) { verdict = 2; break; }
             const int var = kind == K_UNIT ? (lit < 0 ? -lit : lit) : lit;
             if (n_live == 0 || var == 0) { verdict = 1; break; }   // choice()==0: record choices (NDP:817-823)
             evals += (unsigned long long)n_live;                   // one ResolutionStepWithConflict (NDP:831)
@@ -657,19 +672,21 @@ __global__ void dfs_index_kernel(const IndexParams p) {
             ++rebuilds;
         }
         if (verdict == 1) {
-            unsigned long long old = ~0ull;
+            int park = 0;
             if (lane == 0) {
-                old = atomicMin(p.best, g);
+                const unsigned old_piece = atomicMin(p.best_piece + o, q);
+                const unsigned long long old = atomicMin(p.best, g);
                 if (g < old)
                     for (int d = 0; d < p.n_peers; ++d) atomicMin_system(p.peer_best[d], g);
+                park = q < old_piece && g <= old;
             }
-            old = __shfl_sync(kFullMask, old, 0);
-            if (g < old) {   // this warp now holds the lowest-index model: park it in its slot
+            park = __shfl_sync(kFullMask, park, 0);
+            if (park) {   // so far the first model of the lowest SAT subproblem: park it in this warp's slot
                 __syncwarp();
                 __threadfence_block();
                 int32_t* out = p.models + (size_t)gwarp * p.trail_cap;
                 for (int j = lane; j < ntrail; j += 32) out[j] = (int32_t)trail[j];
-                if (lane == 0) { p.model_sub[gwarp] = g; p.model_len[gwarp] = ntrail; }
+                if (lane == 0) { p.model_sub[gwarp] = q; p.model_len[gwarp] = ntrail; }
             }
         }
         if (lane == 0) {

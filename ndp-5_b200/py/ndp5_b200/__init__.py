@@ -48,6 +48,7 @@ def _load():
         "ndp_set_device": (C.c_int, [C.c_int]),
         "ndp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
         "ndp_set_engine": (C.c_int, [C.c_int]),
+        "ndp_set_split": (C.c_int, [C.c_longlong]),
         "ndp_last_error": (C.c_char_p, []),
         "ndp_version": (C.c_char_p, []),
         "ndp_bfs": (C.c_int, [_i32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -90,6 +91,12 @@ def set_engine(e):
     """0 auto, 1 scan, 2 index (or the names)."""
     e = {"auto": 0, "scan": 1, "index": 2}.get(e, e)
     _check(lib.ndp_set_engine(int(e)))
+
+
+def set_split(pieces):
+    """-1 automatic, 0 never split a shard into pieces, > 0 piece target (ndp_set_split)."""
+    pieces = {"auto": -1, "off": 0}.get(pieces, pieces)
+    _check(lib.ndp_set_split(int(pieces)))
 
 
 def device_count():

@@ -11,14 +11,19 @@ import util_cnf
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["index", "scan"])
+@pytest.fixture(scope="module", params=["index", "index-whole", "scan"])
 def nd(request):
-    """Every parity test runs once per DFS engine: both must match the oracle bit for bit."""
+    """Every parity test runs once per DFS engine: all must match the oracle bit for bit.
+    "index" cuts narrow shards into DFS-order pieces (automatic policy: every test frontier is
+    narrower than the device, so the split path is what runs); "index-whole" searches each
+    subproblem with one warp; "scan" is the clause-streaming engine."""
     import ndp5_b200
     assert ndp5_b200.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
-    ndp5_b200.set_engine(request.param)
+    ndp5_b200.set_engine(request.param.split("-")[0])
+    ndp5_b200.set_split("off" if request.param == "index-whole" else "auto")
     yield ndp5_b200
     ndp5_b200.set_engine("auto")
+    ndp5_b200.set_split("auto")
 
 
 def gpu_frontier_list(fr):
