@@ -610,7 +610,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     // persistent level loop (index engine): cooperative launch, one CTA per SM
     bool persist_ok = false, persist_rearm = false;
     size_t persist_cap = 0;
-    DevBuf d_pstate;
+    DevBuf d_pstate, d_pscratch;
     int coop_grid = 0, coop_warps = 0;
     if (use_index && !getenv("NDP_NO_PERSIST")) {
         int coop = 0, sms = 0;
@@ -626,8 +626,9 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_index_persistent_kernel, coop_warps * 32,
                                                                    coop_warps * slot_bytes));
             if (per_sm >= 1) {
-                coop_grid = sms;
+                coop_grid = std::min(sms, 160);   // PersistScratch holds 160 CTA records
                 CUDA_TRY(dev_alloc(&d_pstate.p, sizeof(PersistState)));
+                CUDA_TRY(dev_alloc(&d_pscratch.p, sizeof(PersistScratch)));
                 persist_ok = true;
                 const size_t budget = ((size_t)4 << 30) / slot_bytes;   // <= 4 GB per buffer up front
                 persist_cap = Q > 0 ? std::min<size_t>(2 * (size_t)Q, budget) : std::min<size_t>(8192, budget);
@@ -709,7 +710,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 ps.cap_slots = std::min(f->scap_slots[0], f->scap_slots[1]);
                 ps.cap_nodes = st.node_cap;
                 ps.cap_tree = st.tree_cap;
-                CUDA_TRY(cudaMemcpy(d_pstate.p, &ps, sizeof ps, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpyAsync(d_pstate.p, &ps, sizeof ps, cudaMemcpyHostToDevice, 0));
+                CUDA_TRY(cudaMemsetAsync(d_pscratch.p, 0, sizeof(PersistScratch), 0));
                 IndexRoot ixv = *ix;
                 unsigned *a0 = f->sbuf[0], *a1 = f->sbuf[1];
                 BfsNode *n0 = st.nodes[0], *n1 = st.nodes[1];
@@ -717,7 +719,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 BfsChild* chd = st.children;
                 int Dv = D, Qv = Q, ovrv = ovr ? 1 : 0, maxl = 1 << 20;
                 PersistState* dps = d_pstate.as<PersistState>();
-                void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps};
+                PersistScratch* dsc = d_pscratch.as<PersistScratch>();
+                void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps, &dsc};
                 cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid),
                                                              dim3(coop_warps * 32), args, coop_warps * slot_bytes, 0);
                 if (le == cudaSuccess) le = cudaStreamSynchronize(0);
@@ -726,7 +729,6 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 f->bfs_launches += 1;
                 f->h2d_bytes += sizeof ps;
                 f->d2h_bytes += sizeof ps;
-                if (ps.m < 0) ps.m = -ps.m;   // stop level left untouched for the exact walk below
                 m = (size_t)ps.m; st.cur = ps.cur; cur_buf = ps.cur_buf;
                 it = ps.it; task_count = ps.task_count; f->bfs_evals += ps.evals; st.tree_count = ps.tree_count;
                 n_safe += (size_t)ps.levels_done;

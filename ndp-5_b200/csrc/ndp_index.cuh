@@ -320,15 +320,21 @@ __global__ void __launch_bounds__(1024) bfs_index_trunk_kernel(const IndexRoot i
     if (threadIdx.x == 0) *st_io = st;
 }
 
-// The whole level loop on the device (cooperative launch, one CTA per SM): every level is
-//   expand   one warp per node, grid-stride (index_expand_node)            -> children metadata
+// The whole level loop on the device (cooperative launch, one CTA per SM), ONE grid.sync per level.
+// CTA b owns the contiguous node range [b*B, (b+1)*B) of the level, B = ceil(m / gridDim):
+//   expand    one warp per node (index_expand_node) -> children metadata, 2 open-flags per node
+//   scan      block-wide exclusive scan of the open flags: local queue position of every child
+//   publish   the CTA's totals (open children, expansions, clause evaluations), tagged with the level
+//   look-back warp 0 waits for the totals of CTAs 0..b-1 (all co-resident) -> the CTA's base position
+//   emit      next node list in queue order, choice-tree entries, and the exact -q test "queue size
+//             >= Q before this pop" (NDP:894) evaluated at EVERY node
 //   grid.sync
-//   compact  CTA 0: block-wide scan of the open flags -> next node list, choice tree, counters,
-//            and the exact -q test "queue size >= Q before a pop" (NDP:894) at every node
-//   grid.sync
-// and the kernel returns to the host only when it has to: the level in which a stop test fires
-// (left UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
+//   commit    every CTA derives the same next state (m, iterations, task count, ...) from the same
+//             published totals -- no single-writer commit, no second grid-wide barrier
+// The kernel returns to the host only when it has to: the level in which a stop test fires (left
+// UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
 enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4 };
+constexpr int kPersistMaxBlockNodes = 2048;   // nodes of one level a CTA can own (shared-memory scan arrays)
 struct PersistState {
     int m, cur, cur_buf, levels_done, exit_reason, pad0;
     long long it, task_count;
@@ -337,50 +343,66 @@ struct PersistState {
     // capacities (set by the host)
     unsigned long long cap_slots, cap_nodes, cap_tree;
 };
+struct PersistTotals {            // one per (level parity, CTA); `tag` is written last
+    unsigned children, expanded;
+    unsigned long long evals;
+    unsigned tag, pad;
+};
+struct PersistScratch {           // zeroed by the host before every launch
+    PersistTotals totals[2][160];
+    unsigned stop_tag[2];
+};
 
 __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
                                                                    BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
                                                                    int32_t* ntree1, BfsChild* children,
                                                                    int32_t* tree_parent, int32_t* tree_lit, int D, int Q,
-                                                                   int ovr, int max_levels, PersistState* st) {
+                                                                   int ovr, int max_levels, PersistState* st,
+                                                                   PersistScratch* scratch) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned smem_words[];
-    __shared__ unsigned warp_count[32];
-    __shared__ unsigned long long red_evals[32];
-    __shared__ unsigned red_exp[32];
-    __shared__ unsigned stop_flag, s_running;
+    __shared__ unsigned char s_open[kPersistMaxBlockNodes];       // bit 0: LA open, bit 1: RA open
+    __shared__ unsigned short s_off[kPersistMaxBlockNodes];       // open children of the CTA's earlier nodes
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_children, s_expanded, s_base, s_next_m, s_next_exp, s_stop;
+    __shared__ unsigned long long s_evals, s_next_evals;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    const int total_warps = gridDim.x * warps_per_block;
-    const int gwarp = blockIdx.x * warps_per_block + (int)warp;
+    const int G = gridDim.x, b = blockIdx.x;
     unsigned* S = smem_words + (size_t)warp * ix.slot_words;
-    const unsigned lt = lanemask_lt();
+
+    // the committed state, carried in registers by every thread (identical across the grid)
+    int m = st->m, cur = st->cur, cur_buf = st->cur_buf, levels_done = st->levels_done;
+    long long it = st->it, task_count = st->task_count;
+    unsigned long long evals_total = st->evals, tree_count = st->tree_count;
+    const unsigned long long cap_slots = st->cap_slots, cap_nodes = st->cap_nodes, cap_tree = st->cap_tree;
+    int reason = PEXIT_NONE;
 
     for (int level = 0;; ++level) {
-        // every thread reads the same committed state (written before the last grid.sync)
-        const int m = __ldcg(&st->m), cur = __ldcg(&st->cur), cur_buf = __ldcg(&st->cur_buf);
-        const long long it = __ldcg(&st->it);
-        const unsigned long long tree_count = __ldcg(&st->tree_count);
-        int reason = PEXIT_NONE;
         if (m == 0) reason = PEXIT_EMPTY;
         else if ((Q > 0 && m >= Q) || (D == -1 && !ovr)) reason = PEXIT_HOST_LEVEL;          // NDP:894-897 at the level's first pop
         else if (Q <= 0 && it + m >= (long long)D) reason = PEXIT_HOST_LEVEL;                // the -d budget ends inside this level
-        else if (2ull * m > __ldcg(&st->cap_slots) || 2ull * m > __ldcg(&st->cap_nodes) ||
-                 tree_count + 2ull * m > __ldcg(&st->cap_tree)) reason = PEXIT_CAPACITY;
+        else if (2ull * m > cap_slots || 2ull * m > cap_nodes || tree_count + 2ull * m > cap_tree ||
+                 (m + G - 1) / G > kPersistMaxBlockNodes) reason = PEXIT_CAPACITY;
         else if (level >= max_levels) reason = PEXIT_LEVELS;
-        if (reason != PEXIT_NONE) {
-            if (blockIdx.x == 0 && tid == 0) st->exit_reason = reason;
-            return;   // uniform across the grid: every thread took the same decision from the same state
-        }
+        if (reason != PEXIT_NONE) break;   // uniform: every thread holds the same state
+        const unsigned tag = (unsigned)level + 1u;
+        const int par = level & 1;
         unsigned* src = cur_buf ? sbuf1 : sbuf0;
         unsigned* dst = cur_buf ? sbuf0 : sbuf1;
-        BfsNode* nodes = cur ? nodes1 : nodes0;
-        int32_t* ntree = cur ? ntree1 : ntree0;
+        const BfsNode* nodes = cur ? nodes1 : nodes0;
+        const int32_t* ntree = cur ? ntree1 : ntree0;
         BfsNode* nnodes = cur ? nodes0 : nodes1;
         int32_t* nntree = cur ? ntree0 : ntree1;
+        const int B = (m + G - 1) / G;
+        const int j0 = b * B;
+        const int nb = max(0, min(B, m - j0));         // nodes this CTA owns
+        if (tid == 0) { s_children = 0u; s_expanded = 0u; s_evals = 0ull; }
+        __syncthreads();
         // ---- expand
-        for (int j = gwarp; j < m; j += total_warps) {
+        for (int k = (int)warp; k < nb; k += warps_per_block) {
+            const int j = j0 + k;
             BfsNode nd;
             {
                 const int4 raw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
@@ -388,102 +410,115 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             }
             BfsChild ch[2];
             index_expand_node(ix, src, dst, j, nd, S, lane, ch);
-            if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
+            if (lane == 0) {
+                children[2 * j] = ch[0];
+                children[2 * j + 1] = ch[1];
+                s_open[k] = (unsigned char)((ch[0].n >= 0 ? 1 : 0) | (ch[1].n >= 0 ? 2 : 0));
+                const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+                if (nd.n > 0 && var != 0) { atomicAdd(&s_expanded, 1u); atomicAdd(&s_evals, (unsigned long long)nd.n); }
+            }
         }
-        grid.sync();
-        // ---- compact (CTA 0)
-        if (blockIdx.x == 0) {
-            if (tid == 0) { stop_flag = 0u; s_running = 0u; }
+        __syncthreads();
+        // ---- block-wide exclusive scan of the open-children counts (contiguous chunk per thread)
+        {
+            const int chunk = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
+            const int k0 = (int)tid * chunk, k1 = min(nb, k0 + chunk);
+            unsigned sum = 0;
+            for (int k = k0; k < k1; ++k) sum += (unsigned)__popc((unsigned)s_open[k]);
+            unsigned incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned v = __shfl_up_sync(kFullMask, incl, off);
+                if ((int)lane >= off) incl += v;
+            }
+            if (lane == 31) s_warp[warp] = incl;
             __syncthreads();
-            // Four children per thread and step (two whole nodes), the next step's metadata
-            // prefetched while this one is scanned: the walk is serial in `running` only.
-            unsigned running = 0;
-            const int step = 4 * (int)blockDim.x;
-            int4 nxt[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = 4 * (int)tid + u;
-                nxt[u] = idx < 2 * m ? __ldcg(reinterpret_cast<const int4*>(&children[idx])) : make_int4(-1, 0, 0, 0);
+            unsigned before = 0;
+            for (int w = 0; w < (int)warp; ++w) before += s_warp[w];
+            unsigned run = before + incl - sum;
+            for (int k = k0; k < k1; ++k) { s_off[k] = (unsigned short)run; run += (unsigned)__popc((unsigned)s_open[k]); }
+            if (tid == blockDim.x - 1) s_children = run;
+        }
+        __syncthreads();
+        // ---- publish this CTA's totals, then look back over the earlier CTAs
+        if (warp == 0) {
+            PersistTotals* mine = &scratch->totals[par][b];
+            if (lane == 0) {
+                mine->children = s_children;
+                mine->expanded = s_expanded;
+                mine->evals = s_evals;
+                __threadfence();
+                *(volatile unsigned*)&mine->tag = tag;
             }
-            for (int base = 0; base < 2 * m; base += step) {
-                int4 raw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) raw[u] = nxt[u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = base + step + 4 * (int)tid + u;
-                    nxt[u] = idx < 2 * m ? __ldcg(reinterpret_cast<const int4*>(&children[idx])) : make_int4(-1, 0, 0, 0);
-                }
-                unsigned cnt = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cnt += raw[u].x >= 0 ? 1u : 0u;
-                unsigned incl = cnt;   // inclusive warp scan of the per-thread counts
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const unsigned v = __shfl_up_sync(kFullMask, incl, off);
-                    if ((int)lane >= off) incl += v;
-                }
-                if (lane == 31) warp_count[warp] = incl;
-                __syncthreads();
-                unsigned before = 0, total = 0;
-                for (int w = 0; w < warps_per_block; ++w) {
-                    const unsigned c = warp_count[w];
-                    if (w < (int)warp) before += c;
-                    total += c;
-                }
-                unsigned pos = running + before + incl - cnt;   // open children before this thread's first one
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = base + 4 * (int)tid + u;
-                    if (Q > 0 && idx < 2 * m && (u & 1) == 0 && (unsigned)(m - (idx >> 1)) + pos >= (unsigned)Q) stop_flag = 1u;
-                    if (raw[u].x >= 0) {
-                        const int j = idx >> 1;
-                        const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
-                        const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
-                        BfsNode nn;
-                        nn.slot = (uint32_t)idx; nn.n = raw[u].x; nn.kind = raw[u].y; nn.lit = raw[u].z;
-                        nnodes[pos] = nn;
-                        nntree[pos] = (int32_t)(tree_count + pos);
-                        tree_parent[tree_count + pos] = __ldcg(&ntree[j]);
-                        tree_lit[tree_count + pos] = (idx & 1) ? -var : var;
-                        ++pos;
-                    }
-                }
-                running += total;
-                __syncthreads();
+            unsigned base = 0;
+            for (int c = (int)lane; c < b; c += 32) {
+                const PersistTotals* t = &scratch->totals[par][c];
+                while (*(volatile const unsigned*)&t->tag != tag) { }
+                __threadfence();
+                base += __ldcg(&t->children);
             }
-            unsigned long long evals = 0;
-            unsigned expanded = 0;
-            for (int j = (int)tid; j < m; j += (int)blockDim.x) {
+            base = __reduce_add_sync(kFullMask, base);
+            if (lane == 0) s_base = base;
+        }
+        __syncthreads();
+        // ---- emit: next node list, tree entries, the -q test at every node
+        {
+            const unsigned base = s_base;
+            bool stop = false;
+            for (int i = (int)tid; i < 2 * nb; i += (int)blockDim.x) {
+                const int k = i >> 1, br = i & 1, j = j0 + k;
+                const unsigned open = s_open[k];
+                unsigned pos = base + s_off[k];
+                if (br == 0 && Q > 0 && (unsigned)(m - j) + pos >= (unsigned)Q) stop = true;   // NDP:894 before popping node j
+                if (!(open & (1u << br))) continue;
+                if (br == 1) pos += open & 1u;
+                const BfsChild c = children[2 * j + br];
                 const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
                 const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
-                if (nraw.y > 0 && var != 0) { evals += (unsigned long long)nraw.y; ++expanded; }
+                BfsNode nn;
+                nn.slot = (uint32_t)(2 * j + br); nn.n = c.n; nn.kind = c.kind; nn.lit = c.lit;
+                nnodes[pos] = nn;
+                nntree[pos] = (int32_t)(tree_count + pos);
+                tree_parent[tree_count + pos] = __ldcg(&ntree[j]);
+                tree_lit[tree_count + pos] = br ? -var : var;                                   // LA, RA (NDP:904-925)
             }
-            for (int off = 16; off > 0; off >>= 1) evals += __shfl_down_sync(kFullMask, evals, off);
-            expanded = __reduce_add_sync(kFullMask, expanded);
-            if (lane == 0) { red_evals[warp] = evals; red_exp[warp] = expanded; }
-            __syncthreads();
-            if (tid == 0) {
-                if (stop_flag) {
-                    st->exit_reason = PEXIT_HOST_LEVEL;   // a -q stop fires inside this level: leave it to the host
-                    st->m = -m;                            // sentinel: negative m makes every thread leave below
-                } else {
-                    unsigned long long ev = 0;
-                    unsigned ex = 0;
-                    for (int w = 0; w < warps_per_block; ++w) { ev += red_evals[w]; ex += red_exp[w]; }
-                    st->it = it + ex;                      // NDP:926
-                    st->task_count += running;             // NDP:912,923
-                    st->evals += ev;
-                    st->tree_count = tree_count + running;
-                    st->cur = cur ^ 1;
-                    st->cur_buf = cur_buf ^ 1;
-                    st->m = (int)running;
-                    st->levels_done += 1;
-                }
+            if (stop) *(volatile unsigned*)&scratch->stop_tag[par] = tag;
+        }
+        __threadfence();
+        grid.sync();
+        // ---- commit: every CTA sums the same totals
+        if (warp == 0) {
+            unsigned nm = 0, ne = 0;
+            unsigned long long ev = 0;
+            for (int c = (int)lane; c < G; c += 32) {
+                const PersistTotals* t = &scratch->totals[par][c];
+                nm += __ldcg(&t->children);
+                ne += __ldcg(&t->expanded);
+                ev += __ldcg(&t->evals);
+            }
+            nm = __reduce_add_sync(kFullMask, nm);
+            ne = __reduce_add_sync(kFullMask, ne);
+            for (int off = 16; off > 0; off >>= 1) ev += __shfl_down_sync(kFullMask, ev, off);
+            if (lane == 0) {
+                s_next_m = nm; s_next_exp = ne; s_next_evals = ev;
+                s_stop = __ldcg(&scratch->stop_tag[par]) == tag ? 1u : 0u;
             }
         }
-        grid.sync();
-        if (__ldcg(&st->m) < 0) return;   // stop level (the host restores m = -m); uniform across the grid
+        __syncthreads();
+        if (s_stop) { reason = PEXIT_HOST_LEVEL; break; }   // a -q stop fires inside this level: leave it to the host
+        it += (long long)s_next_exp;                        // NDP:926
+        task_count += (long long)s_next_m;                  // NDP:912,923
+        evals_total += s_next_evals;
+        tree_count += s_next_m;
+        m = (int)s_next_m;
+        cur ^= 1;
+        cur_buf ^= 1;
+        levels_done += 1;
+        __syncthreads();   // s_next_* are rewritten after the next level's grid.sync only, s_children before it
+    }
+    if (b == 0 && tid == 0) {
+        st->m = m; st->cur = cur; st->cur_buf = cur_buf; st->levels_done = levels_done; st->exit_reason = reason;
+        st->it = it; st->task_count = task_count; st->evals = evals_total; st->tree_count = tree_count;
     }
 }
 
