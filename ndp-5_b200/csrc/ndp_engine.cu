@@ -65,6 +65,22 @@ cudaError_t dev_alloc(T** p, size_t bytes) {
 template <class T>
 cudaError_t dev_free(T* p) { return p ? cudaFreeAsync((void*)p, 0) : cudaSuccess; }
 
+// Mapped pinned scratch records (BFS level totals, trunk state): cudaHostAlloc costs about a
+// millisecond, so each (host thread, device, slot) gets one allocation that is kept for the
+// life of the process.
+void* pinned_scratch(int slot, size_t bytes) {
+    struct Item { int device, slot; size_t bytes; void* p; };
+    static thread_local std::vector<Item> items;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Item& it : items)
+        if (it.device == dev && it.slot == slot && it.bytes >= bytes) return it.p;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    items.push_back(Item{dev, slot, bytes, p});
+    return p;
+}
+
 int requested_engine() {
     int e = g_engine;
     if (e == NDP_ENGINE_AUTO) {
@@ -291,29 +307,36 @@ int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
     r.ix.n_zero3 = 0;
     r.ix.first_zero3 = -1;
     {
-        std::vector<std::vector<unsigned>> per_var((size_t)V + 1);
+        // counting sort by variable; within a variable the entries stay in clause order
+        auto merged_entry = [&](size_t c, int j, unsigned& entry) -> bool {
+            const int32_t* l = &f->root_c3[3 * c];
+            if (!l[j]) return false;
+            for (int i = 0; i < j; ++i)
+                if (l[i] && std::abs(l[i]) == std::abs(l[j])) return false;   // one merged entry per (clause, variable)
+            unsigned n_pos = 0, n_neg = 0;
+            for (int i = 0; i < 3; ++i) {
+                if (l[i] == std::abs(l[j])) ++n_pos;
+                if (l[i] == -std::abs(l[j])) ++n_neg;
+            }
+            entry = (unsigned)c | (n_pos << 24) | (n_neg << 26);
+            return true;
+        };
+        unsigned e = 0;
         for (size_t c = 0; c < n_root; ++c) {
             const int32_t* l = &f->root_c3[3 * c];
             root[c] = pack_clause(l[0], l[1], l[2]);
             if (!l[0] && !l[1] && !l[2]) { ++r.ix.n_zero3; if (r.ix.first_zero3 < 0) r.ix.first_zero3 = (int)c; }
-            for (int j = 0; j < 3; ++j) {
-                if (!l[j]) continue;
-                bool seen = false;
-                for (int i = 0; i < j; ++i) seen |= l[i] && std::abs(l[i]) == std::abs(l[j]);
-                if (seen) continue;   // one merged entry per (clause, variable)
-                unsigned n_pos = 0, n_neg = 0;
-                for (int i = 0; i < 3; ++i) {
-                    if (l[i] == std::abs(l[j])) ++n_pos;
-                    if (l[i] == -std::abs(l[j])) ++n_neg;
-                }
-                per_var[(size_t)std::abs(l[j])].push_back((unsigned)c | (n_pos << 24) | (n_neg << 26));
-            }
+            for (int j = 0; j < 3; ++j)
+                if (merged_entry(c, j, e)) ++off[(size_t)std::abs(l[j]) + 1];
         }
-        for (int v = 0; v <= V; ++v) {
-            off[v] = (unsigned)occ.size();
-            occ.insert(occ.end(), per_var[v].begin(), per_var[v].end());
+        for (int v = 0; v <= V; ++v) off[(size_t)v + 1] += off[v];
+        occ.resize(off[(size_t)V + 1]);
+        std::vector<unsigned> cursor(off.begin(), off.end() - 1);
+        for (size_t c = 0; c < n_root; ++c) {
+            const int32_t* l = &f->root_c3[3 * c];
+            for (int j = 0; j < 3; ++j)
+                if (merged_entry(c, j, e)) occ[cursor[(size_t)std::abs(l[j])]++] = e;
         }
-        off[(size_t)V + 1] = (unsigned)occ.size();
     }
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(dev_alloc(&r.d_root, root.size() * sizeof(pclause)));
@@ -359,8 +382,8 @@ struct BfsLevelState {
         if (!totals) {
             // the per-level totals are written straight into mapped pinned host memory: the host
             // only has to wait for the stream, no copy is issued
-            void* h = nullptr;
-            CUDA_TRY(cudaHostAlloc(&h, sizeof(BfsLevelTotals), cudaHostAllocMapped));
+            void* h = pinned_scratch(0, sizeof(BfsLevelTotals));
+            if (!h) return fail(NDP_E_NOMEM, "pinned host scratch");
             h_totals = static_cast<volatile BfsLevelTotals*>(h);
             CUDA_TRY(cudaHostGetDevicePointer((void**)&totals, h, 0));
         }
@@ -399,7 +422,6 @@ struct BfsLevelState {
         if (children) dev_free(children);
         if (tree_parent) dev_free(tree_parent);
         if (tree_lit) dev_free(tree_lit);
-        if (h_totals) cudaFreeHost((void*)h_totals);
     }
 };
 
@@ -596,11 +618,12 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     bool trunk_ok = true;
     volatile TrunkState* h_trunk = nullptr;
     TrunkState* d_trunk = nullptr;
-    struct HostFree { void* p = nullptr; ~HostFree() { if (p) cudaFreeHost(p); } } trunk_mem;
+    struct { void* p = nullptr; } trunk_mem;
     if (use_index && !getenv("NDP_NO_TRUNK")) {
         trunk_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
         if (trunk_warps >= 2) {
-            CUDA_TRY(cudaHostAlloc(&trunk_mem.p, sizeof(TrunkState), cudaHostAllocMapped));
+            trunk_mem.p = pinned_scratch(1, sizeof(TrunkState));
+            if (!trunk_mem.p) return fail(NDP_E_NOMEM, "pinned host scratch");
             h_trunk = static_cast<volatile TrunkState*>(trunk_mem.p);
             CUDA_TRY(cudaHostGetDevicePointer((void**)&d_trunk, trunk_mem.p, 0));
             CUDA_TRY(cudaFuncSetAttribute(bfs_index_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1243,7 +1266,7 @@ size_t split_target(size_t n_sub, int n_warps) {
     if (mode == 0 || n_sub == 0) return 0;
     if (mode > 0) return (size_t)mode > n_sub ? (size_t)mode : 0;
     // auto: only shards that cannot occupy the device (fewer than two subproblems per resident warp)
-    return n_sub < (size_t)2 * n_warps ? (size_t)4 * n_warps : 0;
+    return n_sub < (size_t)2 * n_warps ? (size_t)2 * n_warps : 0;
 }
 
 int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
