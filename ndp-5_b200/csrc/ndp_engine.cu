@@ -633,7 +633,10 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     // persistent level loop (index engine): cooperative launch, one CTA per SM
     bool persist_ok = false, persist_rearm = false;
     size_t persist_cap = 0;
-    DevBuf d_pstate, d_pscratch;
+    DevBuf d_pstate, d_pscratch, d_psnaps, d_ppaths;
+    size_t ppaths_cap = 0;
+    int window_max = 8;
+    if (const char* e = getenv("NDP_BFS_WINDOW")) window_max = std::max(1, std::min(kWindowMax, atoi(e)));
     int coop_grid = 0, coop_warps = 0;
     if (use_index && !getenv("NDP_NO_PERSIST")) {
         int coop = 0, sms = 0;
@@ -652,6 +655,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 coop_grid = std::min(sms, 160);   // PersistScratch holds 160 CTA records
                 CUDA_TRY(dev_alloc(&d_pstate.p, sizeof(PersistState)));
                 CUDA_TRY(dev_alloc(&d_pscratch.p, sizeof(PersistScratch)));
+                if (window_max > 1)   // snapshots of pending RA siblings, one stack per resident warp
+                    CUDA_TRY(dev_alloc(&d_psnaps.p, (size_t)coop_grid * coop_warps * kWindowPend * slot_bytes));
                 persist_ok = true;
                 const size_t budget = ((size_t)4 << 30) / slot_bytes;   // <= 4 GB per buffer up front
                 persist_cap = Q > 0 ? std::min<size_t>(2 * (size_t)Q, budget) : std::min<size_t>(8192, budget);
@@ -743,7 +748,15 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 int Dv = D, Qv = Q, ovrv = ovr ? 1 : 0, maxl = 1 << 20;
                 PersistState* dps = d_pstate.as<PersistState>();
                 PersistScratch* dsc = d_pscratch.as<PersistScratch>();
-                void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps, &dsc};
+                if (window_max > 1 && ppaths_cap < st.node_cap) {   // K choices per output of a window
+                    if (d_ppaths.p) { dev_free(d_ppaths.p); d_ppaths.p = nullptr; }
+                    CUDA_TRY(dev_alloc(&d_ppaths.p, st.node_cap * kWindowMax * sizeof(short)));
+                    ppaths_cap = st.node_cap;
+                }
+                unsigned* snaps = d_psnaps.as<unsigned>();
+                short* ppaths = d_ppaths.as<short>();
+                void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps, &dsc,
+                                &snaps, &ppaths, &window_max};
                 cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid),
                                                              dim3(coop_warps * 32), args, coop_warps * slot_bytes, 0);
                 if (le == cudaSuccess) le = cudaStreamSynchronize(0);
@@ -752,6 +765,9 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 f->bfs_launches += 1;
                 f->h2d_bytes += sizeof ps;
                 f->d2h_bytes += sizeof ps;
+                if (tracing())
+                    fprintf(stderr, "[ndp_bfs] persistent: %d levels, m %zu -> %d, exit %d, windows ok %llu redone %llu (last K %d)\n",
+                            ps.levels_done, m, ps.m, ps.exit_reason, ps.windows_ok, ps.windows_redone, ps.window);
                 m = (size_t)ps.m; st.cur = ps.cur; cur_buf = ps.cur_buf;
                 it = ps.it; task_count = ps.task_count; f->bfs_evals += ps.evals; st.tree_count = ps.tree_count;
                 n_safe += (size_t)ps.levels_done;
@@ -1403,7 +1419,9 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     }
     const size_t nl = split.active ? split.n_pieces : n_sub;         // units the DFS kernel pulls
 
-    DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_bestp, b_msub, b_mlen, b_models, b_scratch;
+    DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_bestp, b_msub, b_mlen, b_models, b_scratch, b_snaps;
+    int snap_depth = 4;
+    if (const char* e = getenv("NDP_DFS_SNAPS")) snap_depth = std::max(0, std::min(32, atoi(e)));
     const size_t nl1 = std::max(nl, (size_t)1);
     CUDA_TRY(dev_alloc(&b_verdict.p, nl1));
     CUDA_TRY(dev_alloc(&b_nodes.p, nl1 * 8));
@@ -1415,6 +1433,12 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(dev_alloc(&b_models.p, (size_t)n_warps * model_stride * 4));
     if (use_index) {
         CUDA_TRY(dev_alloc(&b_scratch.p, (size_t)n_warps * model_stride * sizeof(short)));   // trails
+        if (snap_depth > 0 &&
+            dev_alloc(&b_snaps.p, (size_t)n_warps * snap_depth * ix->slot_words * 4) != cudaSuccess) {
+            cudaGetLastError();   // no room for snapshots: pending siblings are re-derived from the trail
+            b_snaps.p = nullptr;
+            snap_depth = 0;
+        }
         CUDA_TRY(dev_alloc(&b_bestp.p, n_sub * 4));
         CUDA_TRY(cudaMemsetAsync(b_bestp.p, 0xff, n_sub * 4, 0));
     } else if (!plan.smem_w) {
@@ -1459,6 +1483,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.model_sub = b_msub.as<unsigned long long>();
         p.model_len = b_mlen.as<int32_t>();
         p.trails = b_scratch.as<short>();
+        p.snaps = b_snaps.as<unsigned>();
+        p.snap_depth = snap_depth;
         p.models = b_models.as<int32_t>();
         CUDA_TRY(cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
         {

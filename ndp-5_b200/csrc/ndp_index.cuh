@@ -320,32 +320,44 @@ __global__ void __launch_bounds__(1024) bfs_index_trunk_kernel(const IndexRoot i
     if (threadIdx.x == 0) *st_io = st;
 }
 
-// The whole level loop on the device (cooperative launch, one CTA per SM), ONE grid.sync per level.
-// CTA b owns the contiguous node range [b*B, (b+1)*B) of the level, B = ceil(m / gridDim):
-//   expand    one warp per node (index_expand_node) -> children metadata, 2 open-flags per node
-//   scan      block-wide exclusive scan of the open flags: local queue position of every child
-//   publish   the CTA's totals (open children, expansions, clause evaluations), tagged with the level
+// The whole level loop on the device (cooperative launch, one CTA per SM), ONE grid.sync per step.
+// A step advances the queue by K levels (a WINDOW) while no stop test can fire, by one level with
+// the exact tests otherwise.  CTA b owns the contiguous node range [b*B, (b+1)*B) of the level:
+//   expand    one warp per node.  K = 1: index_expand_node -> two children.  K > 1:
+//             index_window_node walks the node's subtree K levels down, LA before RA -- the order
+//             in which those descendants sit in the FIFO queue K levels later (NDP:904-925) -- and
+//             emits up to kWindowFan of them with their K choices; per-level expansion / push /
+//             clause-evaluation counts are accumulated for the reference's counters
+//   scan      block-wide exclusive scan of the per-node output counts: local queue positions
+//   publish   the CTA's totals, tagged with the step
 //   look-back warp 0 waits for the totals of CTAs 0..b-1 (all co-resident) -> the CTA's base position
-//   emit      next node list in queue order, choice-tree entries, and the exact -q test "queue size
-//             >= Q before this pop" (NDP:894) evaluated at EVERY node
+//   emit      next node list in queue order, choice-tree entries; K = 1 also evaluates the exact -q
+//             test "queue size >= Q before this pop" (NDP:894) at EVERY node
 //   grid.sync
-//   commit    every CTA derives the same next state (m, iterations, task count, ...) from the same
-//             published totals -- no single-writer commit, no second grid-wide barrier
+//   commit    every CTA derives the same next state from the same published totals.  A window is
+//             committed only if none of its K levels could have fired a stop test (-q: 2 m < Q at
+//             every level; -d: iterations + m < D) and no node overflowed its fan-out; otherwise it
+//             is redone, shorter, from the untouched source level.
 // The kernel returns to the host only when it has to: the level in which a stop test fires (left
 // UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
 enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4 };
 constexpr int kPersistMaxBlockNodes = 2048;   // nodes of one level a CTA can own (shared-memory scan arrays)
+constexpr int kWindowMax = 16;                // levels per window
+constexpr int kWindowFan = 4;                 // descendants one node may emit per window (else the window is redone)
+constexpr int kWindowPend = 3;                // pending RA siblings one warp can hold (snapshots in global scratch)
 struct PersistState {
-    int m, cur, cur_buf, levels_done, exit_reason, pad0;
+    int m, cur, cur_buf, levels_done, exit_reason, window;
     long long it, task_count;
     unsigned long long evals;
     unsigned long long tree_count;
     // capacities (set by the host)
     unsigned long long cap_slots, cap_nodes, cap_tree;
+    unsigned long long windows_ok, windows_redone;
 };
-struct PersistTotals {            // one per (level parity, CTA); `tag` is written last
-    unsigned children, expanded;
-    unsigned long long evals;
+struct PersistTotals {            // one per (step parity, CTA); `tag` is written last
+    unsigned children, overflow;
+    unsigned expanded[kWindowMax], pushed[kWindowMax], branched[kWindowMax];
+    unsigned long long evals[kWindowMax];
     unsigned tag, pad;
 };
 struct PersistScratch {           // zeroed by the host before every launch
@@ -353,42 +365,145 @@ struct PersistScratch {           // zeroed by the host before every launch
     unsigned stop_tag[2];
 };
 
+// One node, K levels down (K > 1).  Outputs e = 0..count-1 in queue order: state slot
+// dst[kWindowFan * j + e], metadata children[kWindowFan * j + e], choices paths[(kWindowFan * j + e) * kWindowMax + r].
+// Returns the output count, or -1 if the node needs more than kWindowFan outputs / kWindowPend snapshots.
+__device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsigned* src, unsigned* dst, int j,
+                                                 const BfsNode nd, unsigned* S, unsigned* snap, unsigned lane, int K,
+                                                 BfsChild* children, short* paths, unsigned* s_exp, unsigned* s_push,
+                                                 unsigned* s_br, unsigned long long* s_ev) {
+    unsigned* table = S + 3 * ix.bm_words;
+    __syncwarp();
+    slot_load_cg(S, src + (size_t)nd.slot * ix.slot_words, ix.slot_words, lane);
+    __syncwarp();
+    int n_live = nd.n, kind = nd.kind, lit = nd.lit;
+    int r = 0, out = 0, npend = 0;
+    int my_path = 0;                      // lane r holds the choice made at relative level r
+    int pend_r = 0, pend_var = 0, pend_n = 0;   // lane p holds pending entry p
+    for (;;) {
+        bool backtrack = false;
+        if (r == K) {
+            if (out == kWindowFan) return -1;
+            const size_t o = (size_t)kWindowFan * j + out;
+            slot_copy(dst + o * ix.slot_words, S, ix.slot_words, lane);
+            if ((int)lane < K) paths[o * kWindowMax + lane] = (short)my_path;
+            if (lane == 0) { BfsChild c; c.n = n_live; c.kind = kind; c.lit = lit; c.empty = 0; children[o] = c; }
+            ++out;
+            backtrack = true;
+        } else {
+            const int var = kind == K_UNIT ? (lit < 0 ? -lit : lit) : lit;
+            if (n_live <= 0 || var == 0) {
+                backtrack = true;         // choice() == 0: popped, nothing pushed, no iteration (NDP:901-902)
+            } else {
+                if (lane == 0) { atomicAdd(&s_exp[r], 1u); atomicAdd(&s_ev[r], (unsigned long long)n_live); }
+                int t = 0;
+                if (kind == K_UNIT) {
+                    t = lit;              // the other branch falsifies the unit clause: {0,0,0}, never pushed
+                } else {
+                    bool la_conf, ra_conf;
+                    const int la_n = index_assign<false>(ix, S, n_live, var, la_conf, lane);
+                    const int ra_n = index_assign<false>(ix, S, n_live, -var, ra_conf, lane);
+                    const bool la_open = la_n > 0 && !la_conf, ra_open = ra_n > 0 && !ra_conf;   // NDP:908,919
+                    if (la_open && ra_open) {
+                        if (npend == kWindowPend) return -1;
+                        __syncwarp();
+                        slot_copy(snap + (size_t)npend * ix.slot_words, S, ix.slot_words, lane);
+                        if ((int)lane == npend) { pend_r = r; pend_var = var; pend_n = n_live; }
+                        ++npend;
+                        if (lane == 0) { atomicAdd(&s_push[r], 1u); atomicAdd(&s_br[r], 1u); }   // RA is pushed now, visited later
+                        t = var;
+                    } else if (la_open) t = var;
+                    else if (ra_open) t = -var;
+                }
+                if (t == 0) {
+                    backtrack = true;
+                } else {
+                    __syncwarp();
+                    if (lane == 0) table_set(table, t);
+                    bool conflict;
+                    const int n2 = index_assign<true>(ix, S, n_live, t, conflict, lane);
+                    if (n2 > 0 && !conflict) {
+                        if (lane == 0) atomicAdd(&s_push[r], 1u);   // NDP:912,923
+                        if ((int)lane == r) my_path = t;
+                        n_live = n2;
+                        index_choice(ix, S, table, n_live, lane, kind, lit);
+                        ++r;
+                    } else {
+                        backtrack = true; // empty (a dropped solution leaf) or conflict: not pushed
+                    }
+                }
+            }
+        }
+        if (!backtrack) continue;
+        if (npend == 0) break;
+        // the deepest pending RA sibling: restore the state before its branch, take i := false
+        --npend;
+        const int pr = __shfl_sync(kFullMask, pend_r, npend);
+        const int pv = __shfl_sync(kFullMask, pend_var, npend);
+        const int pn = __shfl_sync(kFullMask, pend_n, npend);
+        __syncwarp();
+        slot_load_cg(S, snap + (size_t)npend * ix.slot_words, ix.slot_words, lane);
+        __syncwarp();
+        if (lane == 0) table_set(table, -pv);
+        bool conflict;
+        n_live = index_assign<true>(ix, S, pn, -pv, conflict, lane);   // known open and non-empty
+        if ((int)lane == pr) my_path = -pv;
+        index_choice(ix, S, table, n_live, lane, kind, lit);
+        r = pr + 1;
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
                                                                    BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
                                                                    int32_t* ntree1, BfsChild* children,
                                                                    int32_t* tree_parent, int32_t* tree_lit, int D, int Q,
                                                                    int ovr, int max_levels, PersistState* st,
-                                                                   PersistScratch* scratch) {
+                                                                   PersistScratch* scratch, unsigned* snaps, short* paths,
+                                                                   int window_max) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned smem_words[];
-    __shared__ unsigned char s_open[kPersistMaxBlockNodes];       // bit 0: LA open, bit 1: RA open
-    __shared__ unsigned short s_off[kPersistMaxBlockNodes];       // open children of the CTA's earlier nodes
+    __shared__ unsigned char s_cnt[kPersistMaxBlockNodes];        // K = 1: bit 0 LA open, bit 1 RA open; K > 1: outputs
+    __shared__ unsigned short s_off[kPersistMaxBlockNodes];       // outputs of the CTA's earlier nodes
     __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_children, s_expanded, s_base, s_next_m, s_next_exp, s_stop;
-    __shared__ unsigned long long s_evals, s_next_evals;
+    __shared__ unsigned s_exp[kWindowMax], s_push[kWindowMax], s_br[kWindowMax];
+    __shared__ unsigned long long s_ev[kWindowMax];
+    __shared__ unsigned s_children, s_overflow, s_base, s_stop;
+    __shared__ unsigned t_exp[kWindowMax], t_push[kWindowMax], t_br[kWindowMax], t_children, t_overflow;
+    __shared__ unsigned long long t_ev[kWindowMax];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const int G = gridDim.x, b = blockIdx.x;
     unsigned* S = smem_words + (size_t)warp * ix.slot_words;
+    unsigned* snap = snaps ? snaps + ((size_t)b * warps_per_block + warp) * kWindowPend * ix.slot_words : nullptr;
 
     // the committed state, carried in registers by every thread (identical across the grid)
     int m = st->m, cur = st->cur, cur_buf = st->cur_buf, levels_done = st->levels_done;
     long long it = st->it, task_count = st->task_count;
     unsigned long long evals_total = st->evals, tree_count = st->tree_count;
     const unsigned long long cap_slots = st->cap_slots, cap_nodes = st->cap_nodes, cap_tree = st->cap_tree;
+    unsigned long long windows_ok = 0, windows_redone = 0;
     int reason = PEXIT_NONE;
+    const int Kmax = (snaps && paths) ? min(max(window_max, 1), kWindowMax) : 1;
+    int Kcur = Kmax;
+    bool near_stop = false;   // a window was cut short by the stop rules: finish level by level
 
-    for (int level = 0;; ++level) {
+    for (int step = 0;; ++step) {
         if (m == 0) reason = PEXIT_EMPTY;
         else if ((Q > 0 && m >= Q) || (D == -1 && !ovr)) reason = PEXIT_HOST_LEVEL;          // NDP:894-897 at the level's first pop
         else if (Q <= 0 && it + m >= (long long)D) reason = PEXIT_HOST_LEVEL;                // the -d budget ends inside this level
         else if (2ull * m > cap_slots || 2ull * m > cap_nodes || tree_count + 2ull * m > cap_tree ||
                  (m + G - 1) / G > kPersistMaxBlockNodes) reason = PEXIT_CAPACITY;
-        else if (level >= max_levels) reason = PEXIT_LEVELS;
+        else if (levels_done >= max_levels) reason = PEXIT_LEVELS;
         if (reason != PEXIT_NONE) break;   // uniform: every thread holds the same state
-        const unsigned tag = (unsigned)level + 1u;
-        const int par = level & 1;
+        // window length of this step: K levels need kWindowFan slots / node entries per node and K tree entries per output
+        int K = Kcur;
+        if (K > 1 && ((unsigned long long)kWindowFan * m > cap_slots || (unsigned long long)kWindowFan * m > cap_nodes ||
+                      tree_count + (unsigned long long)kWindowFan * m * K > cap_tree)) K = 1;
+        const int fan = K > 1 ? kWindowFan : 2;
+        const unsigned tag = (unsigned)step + 1u;
+        const int par = step & 1;
         unsigned* src = cur_buf ? sbuf1 : sbuf0;
         unsigned* dst = cur_buf ? sbuf0 : sbuf1;
         const BfsNode* nodes = cur ? nodes1 : nodes0;
@@ -398,7 +513,8 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
         const int B = (m + G - 1) / G;
         const int j0 = b * B;
         const int nb = max(0, min(B, m - j0));         // nodes this CTA owns
-        if (tid == 0) { s_children = 0u; s_expanded = 0u; s_evals = 0ull; }
+        if (tid < kWindowMax) { s_exp[tid] = 0u; s_push[tid] = 0u; s_br[tid] = 0u; s_ev[tid] = 0ull; }
+        if (tid == 0) { s_children = 0u; s_overflow = 0u; }
         __syncthreads();
         // ---- expand
         for (int k = (int)warp; k < nb; k += warps_per_block) {
@@ -408,23 +524,31 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                 const int4 raw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
                 nd.slot = (uint32_t)raw.x; nd.n = raw.y; nd.kind = raw.z; nd.lit = raw.w;
             }
-            BfsChild ch[2];
-            index_expand_node(ix, src, dst, j, nd, S, lane, ch);
-            if (lane == 0) {
-                children[2 * j] = ch[0];
-                children[2 * j + 1] = ch[1];
-                s_open[k] = (unsigned char)((ch[0].n >= 0 ? 1 : 0) | (ch[1].n >= 0 ? 2 : 0));
-                const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
-                if (nd.n > 0 && var != 0) { atomicAdd(&s_expanded, 1u); atomicAdd(&s_evals, (unsigned long long)nd.n); }
+            if (K == 1) {
+                BfsChild ch[2];
+                index_expand_node(ix, src, dst, j, nd, S, lane, ch);
+                if (lane == 0) {
+                    children[2 * j] = ch[0];
+                    children[2 * j + 1] = ch[1];
+                    s_cnt[k] = (unsigned char)((ch[0].n >= 0 ? 1 : 0) | (ch[1].n >= 0 ? 2 : 0));
+                    const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
+                    if (nd.n > 0 && var != 0) { atomicAdd(&s_exp[0], 1u); atomicAdd(&s_ev[0], (unsigned long long)nd.n); }
+                }
+            } else {
+                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, children, paths, s_exp, s_push, s_br, s_ev);
+                if (lane == 0) {
+                    s_cnt[k] = (unsigned char)(c < 0 ? 0 : c);
+                    if (c < 0) s_overflow = 1u;
+                }
             }
         }
         __syncthreads();
-        // ---- block-wide exclusive scan of the open-children counts (contiguous chunk per thread)
+        // ---- block-wide exclusive scan of the per-node output counts (contiguous chunk per thread)
         {
             const int chunk = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
             const int k0 = (int)tid * chunk, k1 = min(nb, k0 + chunk);
             unsigned sum = 0;
-            for (int k = k0; k < k1; ++k) sum += (unsigned)__popc((unsigned)s_open[k]);
+            for (int k = k0; k < k1; ++k) sum += K == 1 ? (unsigned)__popc((unsigned)s_cnt[k]) : (unsigned)s_cnt[k];
             unsigned incl = sum;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -436,20 +560,26 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             unsigned before = 0;
             for (int w = 0; w < (int)warp; ++w) before += s_warp[w];
             unsigned run = before + incl - sum;
-            for (int k = k0; k < k1; ++k) { s_off[k] = (unsigned short)run; run += (unsigned)__popc((unsigned)s_open[k]); }
+            for (int k = k0; k < k1; ++k) {
+                s_off[k] = (unsigned short)run;
+                run += K == 1 ? (unsigned)__popc((unsigned)s_cnt[k]) : (unsigned)s_cnt[k];
+            }
             if (tid == blockDim.x - 1) s_children = run;
         }
         __syncthreads();
         // ---- publish this CTA's totals, then look back over the earlier CTAs
         if (warp == 0) {
             PersistTotals* mine = &scratch->totals[par][b];
-            if (lane == 0) {
-                mine->children = s_children;
-                mine->expanded = s_expanded;
-                mine->evals = s_evals;
-                __threadfence();
-                *(volatile unsigned*)&mine->tag = tag;
+            if (lane < kWindowMax) {
+                mine->expanded[lane] = s_exp[lane];
+                mine->pushed[lane] = s_push[lane];
+                mine->branched[lane] = s_br[lane];
+                mine->evals[lane] = s_ev[lane];
             }
+            if (lane == 0) { mine->children = s_children; mine->overflow = s_overflow; }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *(volatile unsigned*)&mine->tag = tag;
             unsigned base = 0;
             for (int c = (int)lane; c < b; c += 32) {
                 const PersistTotals* t = &scratch->totals[par][c];
@@ -461,64 +591,135 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             if (lane == 0) s_base = base;
         }
         __syncthreads();
-        // ---- emit: next node list, tree entries, the -q test at every node
+        // ---- emit: next node list, tree entries; K = 1: the -q test at every node
         {
             const unsigned base = s_base;
-            bool stop = false;
-            for (int i = (int)tid; i < 2 * nb; i += (int)blockDim.x) {
-                const int k = i >> 1, br = i & 1, j = j0 + k;
-                const unsigned open = s_open[k];
-                unsigned pos = base + s_off[k];
-                if (br == 0 && Q > 0 && (unsigned)(m - j) + pos >= (unsigned)Q) stop = true;   // NDP:894 before popping node j
-                if (!(open & (1u << br))) continue;
-                if (br == 1) pos += open & 1u;
-                const BfsChild c = children[2 * j + br];
-                const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
-                const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
-                BfsNode nn;
-                nn.slot = (uint32_t)(2 * j + br); nn.n = c.n; nn.kind = c.kind; nn.lit = c.lit;
-                nnodes[pos] = nn;
-                nntree[pos] = (int32_t)(tree_count + pos);
-                tree_parent[tree_count + pos] = __ldcg(&ntree[j]);
-                tree_lit[tree_count + pos] = br ? -var : var;                                   // LA, RA (NDP:904-925)
+            if (K == 1) {
+                bool stop = false;
+                for (int i = (int)tid; i < 2 * nb; i += (int)blockDim.x) {
+                    const int k = i >> 1, br = i & 1, j = j0 + k;
+                    const unsigned open = s_cnt[k];
+                    unsigned pos = base + s_off[k];
+                    if (br == 0 && Q > 0 && (unsigned)(m - j) + pos >= (unsigned)Q) stop = true;   // NDP:894 before popping node j
+                    if (!(open & (1u << br))) continue;
+                    if (br == 1) pos += open & 1u;
+                    const BfsChild c = children[2 * j + br];
+                    const int4 nraw = __ldcg(reinterpret_cast<const int4*>(&nodes[j]));
+                    const int var = nraw.z == K_UNIT ? (nraw.w < 0 ? -nraw.w : nraw.w) : nraw.w;
+                    BfsNode nn;
+                    nn.slot = (uint32_t)(2 * j + br); nn.n = c.n; nn.kind = c.kind; nn.lit = c.lit;
+                    nnodes[pos] = nn;
+                    nntree[pos] = (int32_t)(tree_count + pos);
+                    tree_parent[tree_count + pos] = __ldcg(&ntree[j]);
+                    tree_lit[tree_count + pos] = br ? -var : var;                               // LA, RA (NDP:904-925)
+                }
+                if (stop) *(volatile unsigned*)&scratch->stop_tag[par] = tag;
+            } else {
+                // one thread per (node, output, relative level): K chained tree entries per output
+                const int per_node = kWindowFan * K;
+                for (int i = (int)tid; i < nb * per_node; i += (int)blockDim.x) {
+                    const int k = i / per_node, rem = i - k * per_node, e = rem / K, r = rem - e * K, j = j0 + k;
+                    if (e >= (int)s_cnt[k]) continue;
+                    const unsigned pos = base + s_off[k] + (unsigned)e;
+                    const size_t o = (size_t)kWindowFan * j + e;
+                    const unsigned long long t0 = tree_count + (unsigned long long)pos * K;
+                    tree_parent[t0 + r] = r == 0 ? __ldcg(&ntree[j]) : (int32_t)(t0 + r - 1);
+                    tree_lit[t0 + r] = (int32_t)paths[o * kWindowMax + r];
+                    if (r == K - 1) {
+                        const BfsChild c = children[o];
+                        BfsNode nn;
+                        nn.slot = (uint32_t)o; nn.n = c.n; nn.kind = c.kind; nn.lit = c.lit;
+                        nnodes[pos] = nn;
+                        nntree[pos] = (int32_t)(t0 + K - 1);
+                    }
+                }
             }
-            if (stop) *(volatile unsigned*)&scratch->stop_tag[par] = tag;
         }
         __threadfence();
         grid.sync();
         // ---- commit: every CTA sums the same totals
         if (warp == 0) {
-            unsigned nm = 0, ne = 0;
-            unsigned long long ev = 0;
+            unsigned nm = 0, ov = 0;
             for (int c = (int)lane; c < G; c += 32) {
                 const PersistTotals* t = &scratch->totals[par][c];
                 nm += __ldcg(&t->children);
-                ne += __ldcg(&t->expanded);
-                ev += __ldcg(&t->evals);
+                ov |= __ldcg(&t->overflow);
             }
             nm = __reduce_add_sync(kFullMask, nm);
-            ne = __reduce_add_sync(kFullMask, ne);
-            for (int off = 16; off > 0; off >>= 1) ev += __shfl_down_sync(kFullMask, ev, off);
+            ov = __reduce_or_sync(kFullMask, ov);
+            for (int r = 0; r < K; ++r) {
+                unsigned ne = 0, np = 0, nbr = 0;
+                unsigned long long ev = 0;
+                for (int c = (int)lane; c < G; c += 32) {
+                    const PersistTotals* t = &scratch->totals[par][c];
+                    ne += __ldcg(&t->expanded[r]);
+                    np += __ldcg(&t->pushed[r]);
+                    nbr += __ldcg(&t->branched[r]);
+                    ev += __ldcg(&t->evals[r]);
+                }
+                ne = __reduce_add_sync(kFullMask, ne);
+                np = __reduce_add_sync(kFullMask, np);
+                nbr = __reduce_add_sync(kFullMask, nbr);
+                for (int off = 16; off > 0; off >>= 1) ev += __shfl_down_sync(kFullMask, ev, off);
+                if (lane == 0) { t_exp[r] = ne; t_push[r] = np; t_br[r] = nbr; t_ev[r] = ev; }
+            }
             if (lane == 0) {
-                s_next_m = nm; s_next_exp = ne; s_next_evals = ev;
+                t_children = nm; t_overflow = ov;
                 s_stop = __ldcg(&scratch->stop_tag[par]) == tag ? 1u : 0u;
             }
         }
         __syncthreads();
-        if (s_stop) { reason = PEXIT_HOST_LEVEL; break; }   // a -q stop fires inside this level: leave it to the host
-        it += (long long)s_next_exp;                        // NDP:926
-        task_count += (long long)s_next_m;                  // NDP:912,923
-        evals_total += s_next_evals;
-        tree_count += s_next_m;
-        m = (int)s_next_m;
-        cur ^= 1;
-        cur_buf ^= 1;
-        levels_done += 1;
-        __syncthreads();   // s_next_* are rewritten after the next level's grid.sync only, s_children before it
+        if (K == 1) {
+            if (s_stop) { reason = PEXIT_HOST_LEVEL; break; }   // a -q stop fires inside this level: leave it to the host
+            it += (long long)t_exp[0];                          // NDP:926
+            task_count += (long long)t_children;                // NDP:912,923
+            evals_total += t_ev[0];
+            tree_count += t_children;
+            m = (int)t_children;
+            cur ^= 1;
+            cur_buf ^= 1;
+            levels_done += 1;
+            if (!near_stop && Kcur < Kmax) Kcur = min(Kmax, Kcur * 2);   // regrow after a fan-out overflow
+        } else {
+            // How many of the window's levels are certain to have run without any stop test firing.
+            // -q (NDP:894): the queue holds m_r entries when level r starts and moves by (children - 1)
+            // per pop, so it never exceeds m_r + (nodes of the level with two open children).
+            // -d (NDP:935): the level is consumed whole iff iterations + m_r < D.
+            int valid = 0;
+            long long it_r = it;
+            long long m_r = m;
+            for (int r = 0; r < K; ++r) {
+                const bool ok = m_r == 0 || (Q > 0 ? m_r + (long long)t_br[r] < (long long)Q : it_r + m_r < (long long)D);
+                if (!ok) break;
+                it_r += (long long)t_exp[r];
+                m_r = (long long)t_push[r];
+                ++valid;
+            }
+            if (valid == K && !t_overflow) {
+                long long pushes = 0;
+                for (int r = 0; r < K; ++r) { pushes += (long long)t_push[r]; evals_total += t_ev[r]; }
+                it = it_r;
+                task_count += pushes;
+                tree_count += (unsigned long long)t_children * K;
+                m = (int)t_children;
+                cur ^= 1;
+                cur_buf ^= 1;
+                levels_done += K;
+                ++windows_ok;
+                if (!near_stop) Kcur = min(Kmax, Kcur * 2);
+            } else {
+                // redo from the untouched source level with a shorter window
+                ++windows_redone;
+                if (valid < K) { near_stop = true; Kcur = max(1, valid); }
+                if (t_overflow) Kcur = max(1, min(Kcur, K / 2));
+            }
+        }
+        __syncthreads();   // the shared totals are rewritten by the next step
     }
     if (b == 0 && tid == 0) {
         st->m = m; st->cur = cur; st->cur_buf = cur_buf; st->levels_done = levels_done; st->exit_reason = reason;
         st->it = it; st->task_count = task_count; st->evals = evals_total; st->tree_count = tree_count;
+        st->windows_ok = windows_ok; st->windows_redone = windows_redone; st->window = Kcur;
     }
 }
 
@@ -592,6 +793,8 @@ struct IndexParams {
     unsigned int* rebuilds;
     unsigned long long* model_sub;    // [n_warps] PIECE whose model the warp parked
     int32_t* model_len;               // [n_warps]
+    unsigned* snaps;                  // [n_warps][snap_depth] state slots saved at decisions with a pending LA sibling
+    int snap_depth;                   //   (0: always re-derive the sibling from the trail)
     short* trails;                    // [n_warps][trail_cap] working trail of each warp
     int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
     int warp_bytes, off_pend;         // shared memory of one warp: state slot, then pend
@@ -608,6 +811,7 @@ __global__ void dfs_index_kernel(const IndexParams p) {
     unsigned* table = B + 3 * ix.bm_words;
     unsigned* pend = reinterpret_cast<unsigned*>(mine + p.off_pend);
     short* trail = p.trails + (size_t)gwarp * p.trail_cap;
+    unsigned* snap = p.snaps + (size_t)gwarp * p.snap_depth * ix.slot_words;
 
     for (;;) {
         unsigned q = 0;
@@ -628,6 +832,7 @@ __global__ void dfs_index_kernel(const IndexParams p) {
         unsigned long long nodes = 0, evals = 0;
         unsigned rebuilds = 0;
         int verdict = 0;
+        int npend = 0, snap_low = 0, snap_n = 0;   // pending siblings; lowest one whose snapshot is intact; lane k: |A| of snapshot k
         __syncwarp();
         if (kind != K_LEAF) {
             slot_copy(B, slot, ix.slot_words, lane);
@@ -663,6 +868,17 @@ __global__ void dfs_index_kernel(const IndexParams p) {
             }
             bool dead = t == 0;
             if (!dead) {
+                if (pending) {
+                    // keep the state before the branch: the LA sibling is one resolution step away from it
+                    if (p.snap_depth > 0) {
+                        const int k = npend % p.snap_depth;
+                        __syncwarp();
+                        slot_copy(snap + (size_t)k * ix.slot_words, B, ix.slot_words, lane);
+                        if ((int)lane == k) snap_n = n_live;
+                        snap_low = max(min(snap_low, npend), npend - p.snap_depth + 1);
+                    }
+                    ++npend;
+                }
                 if (lane == 0) {
                     if (pending) pend[ntrail >> 5] |= 1u << (ntrail & 31);
                     trail[ntrail] = (short)t;
@@ -693,6 +909,23 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 trail[pos] = (short)(-trail[pos]);   // -i -> +i : now the LA sibling
             }
             ntrail = pos + 1;
+            --npend;
+            ++rebuilds;
+            if (p.snap_depth > 0 && npend >= snap_low) {
+                const int k = npend % p.snap_depth;
+                __syncwarp();
+                __threadfence_block();
+                slot_copy(B, snap + (size_t)k * ix.slot_words, ix.slot_words, lane);
+                const int la = (int)trail[pos];
+                const int n_before = __shfl_sync(kFullMask, snap_n, k);
+                __syncwarp();
+                if (lane == 0) table_set(table, la);
+                bool conflict;
+                n_live = index_assign<true>(ix, B, n_before, la, conflict, lane);   // open and non-empty: it was left pending
+                index_choice(ix, B, table, n_live, lane, kind, lit);
+                continue;
+            }
+            snap_low = min(snap_low, npend);   // siblings pushed from here on have intact snapshots again
             for (int w = lane; w < ix.table_words; w += 32) table[w] = __ldg(&slot[3 * ix.bm_words + w]);
             __syncwarp();
             __threadfence_block();
@@ -704,7 +937,6 @@ __global__ void dfs_index_kernel(const IndexParams p) {
             __syncwarp();
             n_live = index_rebuild(ix, B, table, lane);
             index_choice(ix, B, table, n_live, lane, kind, lit);
-            ++rebuilds;
         }
         if (verdict == 1) {
             int park = 0;
