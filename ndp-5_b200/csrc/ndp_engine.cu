@@ -635,7 +635,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     size_t persist_cap = 0;
     DevBuf d_pstate, d_pscratch, d_psnaps, d_ppaths;
     size_t ppaths_cap = 0;
-    int window_max = 8;
+    int window_max = kWindowMax;
     if (const char* e = getenv("NDP_BFS_WINDOW")) window_max = std::max(1, std::min(kWindowMax, atoi(e)));
     int coop_grid = 0, coop_warps = 0;
     if (use_index && !getenv("NDP_NO_PERSIST")) {
@@ -766,8 +766,10 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 f->h2d_bytes += sizeof ps;
                 f->d2h_bytes += sizeof ps;
                 if (tracing())
-                    fprintf(stderr, "[ndp_bfs] persistent: %d levels, m %zu -> %d, exit %d, windows ok %llu redone %llu (last K %d)\n",
-                            ps.levels_done, m, ps.m, ps.exit_reason, ps.windows_ok, ps.windows_redone, ps.window);
+                    fprintf(stderr, "[ndp_bfs] persistent: %d levels, m %zu -> %d, exit %d, windows ok %llu redone %llu (last K %d) | "
+                                    "CTA 0: expand %.2f, scan+look-back %.2f, emit %.2f, grid.sync %.2f, commit %.2f ms\n",
+                            ps.levels_done, m, ps.m, ps.exit_reason, ps.windows_ok, ps.windows_redone, ps.window,
+                            ps.t_phase[0] / 1e6, ps.t_phase[1] / 1e6, ps.t_phase[2] / 1e6, ps.t_phase[3] / 1e6, ps.t_phase[4] / 1e6);
                 m = (size_t)ps.m; st.cur = ps.cur; cur_buf = ps.cur_buf;
                 it = ps.it; task_count = ps.task_count; f->bfs_evals += ps.evals; st.tree_count = ps.tree_count;
                 n_safe += (size_t)ps.levels_done;

@@ -353,15 +353,24 @@ struct PersistState {
     // capacities (set by the host)
     unsigned long long cap_slots, cap_nodes, cap_tree;
     unsigned long long windows_ok, windows_redone;
+    unsigned long long t_phase[5];   // CTA 0, ns: expand | scan + publish + look-back | emit | grid.sync | commit
 };
-struct PersistTotals {            // one per (step parity, CTA); `tag` is written last
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct PersistTotals {            // one per (step parity, CTA): what the look-back needs; `tag` is written last
+    unsigned children, tag;
+};
+struct PersistAcc {               // grid-wide sums of one step, accumulated with atomics (three in rotation)
     unsigned children, overflow;
     unsigned expanded[kWindowMax], pushed[kWindowMax], branched[kWindowMax];
     unsigned long long evals[kWindowMax];
-    unsigned tag, pad;
 };
 struct PersistScratch {           // zeroed by the host before every launch
     PersistTotals totals[2][160];
+    PersistAcc acc[3];
     unsigned stop_tag[2];
 };
 
@@ -370,8 +379,9 @@ struct PersistScratch {           // zeroed by the host before every launch
 // Returns the output count, or -1 if the node needs more than kWindowFan outputs / kWindowPend snapshots.
 __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsigned* src, unsigned* dst, int j,
                                                  const BfsNode nd, unsigned* S, unsigned* snap, unsigned lane, int K,
-                                                 BfsChild* children, short* paths, unsigned* s_exp, unsigned* s_push,
-                                                 unsigned* s_br, unsigned long long* s_ev) {
+                                                 BfsChild* children, short* paths, unsigned& my_exp, unsigned& my_push,
+                                                 unsigned& my_br, unsigned long long& my_ev) {
+    // my_*: lane r accumulates the counters of relative level r (summed over the warp's nodes by the caller)
     unsigned* table = S + 3 * ix.bm_words;
     __syncwarp();
     slot_load_cg(S, src + (size_t)nd.slot * ix.slot_words, ix.slot_words, lane);
@@ -395,7 +405,7 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
             if (n_live <= 0 || var == 0) {
                 backtrack = true;         // choice() == 0: popped, nothing pushed, no iteration (NDP:901-902)
             } else {
-                if (lane == 0) { atomicAdd(&s_exp[r], 1u); atomicAdd(&s_ev[r], (unsigned long long)n_live); }
+                if ((int)lane == r) { ++my_exp; my_ev += (unsigned long long)n_live; }
                 int t = 0;
                 if (kind == K_UNIT) {
                     t = lit;              // the other branch falsifies the unit clause: {0,0,0}, never pushed
@@ -410,7 +420,7 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
                         slot_copy(snap + (size_t)npend * ix.slot_words, S, ix.slot_words, lane);
                         if ((int)lane == npend) { pend_r = r; pend_var = var; pend_n = n_live; }
                         ++npend;
-                        if (lane == 0) { atomicAdd(&s_push[r], 1u); atomicAdd(&s_br[r], 1u); }   // RA is pushed now, visited later
+                        if ((int)lane == r) { ++my_push; ++my_br; }   // RA is pushed now, visited later
                         t = var;
                     } else if (la_open) t = var;
                     else if (ra_open) t = -var;
@@ -423,7 +433,7 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
                     bool conflict;
                     const int n2 = index_assign<true>(ix, S, n_live, t, conflict, lane);
                     if (n2 > 0 && !conflict) {
-                        if (lane == 0) atomicAdd(&s_push[r], 1u);   // NDP:912,923
+                        if ((int)lane == r) ++my_push;   // NDP:912,923
                         if ((int)lane == r) my_path = t;
                         n_live = n2;
                         index_choice(ix, S, table, n_live, lane, kind, lit);
@@ -484,6 +494,8 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
     unsigned long long evals_total = st->evals, tree_count = st->tree_count;
     const unsigned long long cap_slots = st->cap_slots, cap_nodes = st->cap_nodes, cap_tree = st->cap_tree;
     unsigned long long windows_ok = 0, windows_redone = 0;
+    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tmark = 0;   // phase clocks (thread 0 of CTA 0)
+    const bool clocked = b == 0 && tid == 0;
     int reason = PEXIT_NONE;
     const int Kmax = (snaps && paths) ? min(max(window_max, 1), kWindowMax) : 1;
     int Kcur = Kmax;
@@ -516,7 +528,10 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
         if (tid < kWindowMax) { s_exp[tid] = 0u; s_push[tid] = 0u; s_br[tid] = 0u; s_ev[tid] = 0ull; }
         if (tid == 0) { s_children = 0u; s_overflow = 0u; }
         __syncthreads();
+        if (clocked) tmark = global_ns();
         // ---- expand
+        unsigned my_exp = 0, my_push = 0, my_br = 0;   // window mode: lane r counts relative level r
+        unsigned long long my_ev = 0;
         for (int k = (int)warp; k < nb; k += warps_per_block) {
             const int j = j0 + k;
             BfsNode nd;
@@ -535,14 +550,21 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                     if (nd.n > 0 && var != 0) { atomicAdd(&s_exp[0], 1u); atomicAdd(&s_ev[0], (unsigned long long)nd.n); }
                 }
             } else {
-                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, children, paths, s_exp, s_push, s_br, s_ev);
+                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, children, paths, my_exp, my_push, my_br, my_ev);
                 if (lane == 0) {
                     s_cnt[k] = (unsigned char)(c < 0 ? 0 : c);
                     if (c < 0) s_overflow = 1u;
                 }
             }
         }
+        if (K > 1 && (int)lane < K && my_exp) {
+            atomicAdd(&s_exp[lane], my_exp);
+            atomicAdd(&s_push[lane], my_push);
+            atomicAdd(&s_br[lane], my_br);
+            atomicAdd(&s_ev[lane], my_ev);
+        }
         __syncthreads();
+        if (clocked) { const unsigned long long t = global_ns(); tp0 += t - tmark; tmark = t; }
         // ---- block-wide exclusive scan of the per-node output counts (contiguous chunk per thread)
         {
             const int chunk = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -570,16 +592,20 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
         // ---- publish this CTA's totals, then look back over the earlier CTAs
         if (warp == 0) {
             PersistTotals* mine = &scratch->totals[par][b];
-            if (lane < kWindowMax) {
-                mine->expanded[lane] = s_exp[lane];
-                mine->pushed[lane] = s_push[lane];
-                mine->branched[lane] = s_br[lane];
-                mine->evals[lane] = s_ev[lane];
+            PersistAcc* acc = &scratch->acc[step % 3];
+            if ((int)lane < K && s_exp[lane]) {
+                atomicAdd(&acc->expanded[lane], s_exp[lane]);
+                if (s_push[lane]) atomicAdd(&acc->pushed[lane], s_push[lane]);
+                if (s_br[lane]) atomicAdd(&acc->branched[lane], s_br[lane]);
+                atomicAdd(&acc->evals[lane], s_ev[lane]);
             }
-            if (lane == 0) { mine->children = s_children; mine->overflow = s_overflow; }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) *(volatile unsigned*)&mine->tag = tag;
+            if (lane == 0) {
+                if (s_children) atomicAdd(&acc->children, s_children);
+                if (s_overflow) atomicOr(&acc->overflow, 1u);
+                mine->children = s_children;
+                __threadfence();
+                *(volatile unsigned*)&mine->tag = tag;
+            }
             unsigned base = 0;
             for (int c = (int)lane; c < b; c += 32) {
                 const PersistTotals* t = &scratch->totals[par][c];
@@ -591,6 +617,7 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             if (lane == 0) s_base = base;
         }
         __syncthreads();
+        if (clocked) { const unsigned long long t = global_ns(); tp1 += t - tmark; tmark = t; }
         // ---- emit: next node list, tree entries; K = 1: the -q test at every node
         {
             const unsigned base = s_base;
@@ -636,37 +663,25 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             }
         }
         __threadfence();
+        if (clocked) { const unsigned long long t = global_ns(); tp2 += t - tmark; tmark = t; }
         grid.sync();
-        // ---- commit: every CTA sums the same totals
-        if (warp == 0) {
-            unsigned nm = 0, ov = 0;
-            for (int c = (int)lane; c < G; c += 32) {
-                const PersistTotals* t = &scratch->totals[par][c];
-                nm += __ldcg(&t->children);
-                ov |= __ldcg(&t->overflow);
-            }
-            nm = __reduce_add_sync(kFullMask, nm);
-            ov = __reduce_or_sync(kFullMask, ov);
-            for (int r = 0; r < K; ++r) {
-                unsigned ne = 0, np = 0, nbr = 0;
-                unsigned long long ev = 0;
-                for (int c = (int)lane; c < G; c += 32) {
-                    const PersistTotals* t = &scratch->totals[par][c];
-                    ne += __ldcg(&t->expanded[r]);
-                    np += __ldcg(&t->pushed[r]);
-                    nbr += __ldcg(&t->branched[r]);
-                    ev += __ldcg(&t->evals[r]);
-                }
-                ne = __reduce_add_sync(kFullMask, ne);
-                np = __reduce_add_sync(kFullMask, np);
-                nbr = __reduce_add_sync(kFullMask, nbr);
-                for (int off = 16; off > 0; off >>= 1) ev += __shfl_down_sync(kFullMask, ev, off);
-                if (lane == 0) { t_exp[r] = ne; t_push[r] = np; t_br[r] = nbr; t_ev[r] = ev; }
-            }
-            if (lane == 0) {
-                t_children = nm; t_overflow = ov;
+        if (clocked) { const unsigned long long t = global_ns(); tp3 += t - tmark; tmark = t; }
+        // ---- commit: every CTA reads the same grid-wide sums
+        if (tid < (unsigned)K) {
+            const PersistAcc* acc = &scratch->acc[step % 3];
+            t_exp[tid] = __ldcg(&acc->expanded[tid]);
+            t_push[tid] = __ldcg(&acc->pushed[tid]);
+            t_br[tid] = __ldcg(&acc->branched[tid]);
+            t_ev[tid] = __ldcg(&acc->evals[tid]);
+            if (tid == 0) {
+                t_children = __ldcg(&acc->children);
+                t_overflow = __ldcg(&acc->overflow);
                 s_stop = __ldcg(&scratch->stop_tag[par]) == tag ? 1u : 0u;
             }
+        }
+        if (b == 0 && tid >= 32 && tid < 32 + sizeof(PersistAcc) / 4) {
+            // clear the accumulator of step + 2: last read before this step's barrier, next written after the next one
+            reinterpret_cast<unsigned*>(&scratch->acc[(step + 2) % 3])[tid - 32] = 0u;
         }
         __syncthreads();
         if (K == 1) {
@@ -715,11 +730,13 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             }
         }
         __syncthreads();   // the shared totals are rewritten by the next step
+        if (clocked) { const unsigned long long t = global_ns(); tp4 += t - tmark; tmark = t; }
     }
     if (b == 0 && tid == 0) {
         st->m = m; st->cur = cur; st->cur_buf = cur_buf; st->levels_done = levels_done; st->exit_reason = reason;
         st->it = it; st->task_count = task_count; st->evals = evals_total; st->tree_count = tree_count;
         st->windows_ok = windows_ok; st->windows_redone = windows_redone; st->window = Kcur;
+        st->t_phase[0] = tp0; st->t_phase[1] = tp1; st->t_phase[2] = tp2; st->t_phase[3] = tp3; st->t_phase[4] = tp4;
     }
 }
 
