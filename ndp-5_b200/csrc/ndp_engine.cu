@@ -1607,6 +1607,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
             if (h_msub[w] == win_piece) {
                 found = true;
                 if ((rc = frontier_choices(f, win, *model))) return rc;   // choices_k ++ dfs choices (NDP:1430-1431)
+                CUDA_TRY(cudaSetDevice(device));                          // (the tree lives on the frontier's home device)
                 if (split.active) {
                     // ... ++ the choices the split made on the way to the winning piece
                     const int cap = std::max(f->max_var, 1) + 8;
@@ -1634,7 +1635,9 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
                 model->insert(model->end(), tail.begin(), tail.end());
                 d2h += tail.size() * 4;
             }
-        if (!found) return fail(NDP_E_CUDA, "the winning piece's model was not parked");
+        // not found: a lower SAT index was already known (exit_flag hint / a peer device), so this
+        // shard's own winner never parked its trail -- the job's model comes from that other shard
+        if (!found) model->clear();
     }
     if (stats) {
         stats->h2d_bytes += 8 + 4;                                   // early-exit word + work counter
