@@ -306,3 +306,35 @@ def test_single_subproblem_32bit_d12(nd, oracle, golden, cnf_text):
     d1, d2 = util_cnf.decode_factors(r["model"], v1, v2)
     assert {d1, d2} == {45887, 54493}
     fr.free()
+
+
+def test_full_size_48bit_and_64bit(nd, oracle, cnf_text, request):
+    """BASELINE configs[2] and [3] at full size.  The reference cannot finish these searches on host
+    cores, so parity rests on (a) the BFS counters it did produce (48-bit -q 4096 ->
+    395 680 expansions / 399 776 tasks, 4096 x 9934 clauses; 64-bit -q 4096 -> 395 696 / 399 792,
+    4096 x 20 014 clauses, 643 choices) and (b) size-independent properties: the model satisfies the
+    ORIGINAL CNF and its decoded factors multiply to N; both engines agree on the winner."""
+    import re
+    A = oracle.parse(cnf_text("rsaFACT-64bit"))
+    fr = nd.bfs(A, 0, True, 4096)
+    assert (fr.iterations, fr.task_count, len(fr)) == (395696, 399792, 4096)
+    assert fr.dims(0) == (20014, 643) and fr.dims(4095)[0] == 20014
+    fr.free()
+    text = cnf_text("rsaFACT-48bit")
+    A = oracle.parse(text)
+    fr = nd.bfs(A, 0, True, 4096)
+    assert (fr.iterations, fr.task_count, len(fr)) == (395680, 399776, 4096)
+    assert fr.dims(0) == (9934, 627)
+    cl, ch = fr.get(17)
+    o = oracle.bfs(A, 0, True, 64)          # a prefix the oracle finishes quickly, for the clause-list format
+    assert len(o["frontier"]) == 64 and cl.shape == (9934, 3) and ch.shape == (627,)
+    if request.node.callspec.params["nd"] != "scan":   # 4.1e8 nodes: the streaming engine holds 2 warps/SM at this size
+        r = fr.dfs_shard(early_exit=True)
+        assert r["winner"] == 301
+        assert util_cnf.satisfies(A, r["model"])
+        v1 = [int(x) for x in re.search(r"first input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+        v2 = [int(x) for x in re.search(r"second input \[msb,...,lsb\]: \[(.*?)\]", text).group(1).split(",")]
+        d1, d2 = util_cnf.decode_factors(r["model"], v1, v2)
+        assert d1 * d2 == 209727620799133 and {d1, d2} == {15908531, 13183343}
+        assert (r["verdict"][:301] == 0).all() and r["verdict"][301] == 1
+    fr.free()
