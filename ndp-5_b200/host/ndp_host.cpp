@@ -57,8 +57,9 @@ bool next_int(const char*& p, const char* end, int& out) {
 }
 }  // namespace
 
-std::vector<int32_t> parse_dimacs(const std::string& text) {
+std::vector<int32_t> parse_dimacs(const std::string& text, DimacsDiagnostics* diag) {
     std::vector<int32_t> out;
+    if (diag) *diag = DimacsDiagnostics();
     const char* p = text.data();
     const char* end = p + text.size();
     while (p < end) {
@@ -75,6 +76,13 @@ std::vector<int32_t> parse_dimacs(const std::string& text) {
             }
             if (n == 1) { out.push_back(0); out.push_back(0); out.push_back(lits[0]); }        // NDP:632-634
             else if (n == 3) { out.push_back(lits[0]); out.push_back(lits[1]); out.push_back(lits[2]); }  // NDP:635-637
+            else if (diag) {                                                                    // NDP:639: dropped without a word
+                if (n == 0) ++diag->empty_lines;
+                else {
+                    if (!diag->dropped) diag->first_dropped_width = n;
+                    ++diag->dropped;
+                }
+            }
         }
         p = eol + 1;
     }

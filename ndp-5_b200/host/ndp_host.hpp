@@ -15,7 +15,14 @@ namespace ndph {
 // ---- input ----------------------------------------------------------------------------------
 // parseDimacsString, NDP:619-642: one clause per line; lines that are empty or start with 'c'/'p'
 // are skipped; 1 literal -> {0,0,x}; 3 literals -> {x,y,z}; any other width is silently dropped.
-std::vector<int32_t> parse_dimacs(const std::string& text);   // n x 3 row-major
+// What the reference's parser does not tell its user: clause lines whose width is neither 1 nor 3
+// are dropped (NDP:639), which silently changes the formula being solved.
+struct DimacsDiagnostics {
+    size_t dropped = 0;               // clause lines with 2 or > 3 literals
+    size_t first_dropped_width = 0;
+    size_t empty_lines = 0;           // lines holding only the terminating 0
+};
+std::vector<int32_t> parse_dimacs(const std::string& text, DimacsDiagnostics* diag = nullptr);   // n x 3 row-major
 
 struct Header {
     bool ok_problem = false, ok_product = false;

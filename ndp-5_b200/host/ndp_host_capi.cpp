@@ -20,6 +20,13 @@ size_t ndph_parse_dimacs(const char* text, int32_t* out3, size_t cap_clauses) {
     if (out3 && c.size() / 3 <= cap_clauses) memcpy(out3, c.data(), c.size() * sizeof(int32_t));
     return c.size() / 3;
 }
+// how many clause lines parse_dimacs dropped for their width (NDP:639), and the first such width
+size_t ndph_dimacs_dropped(const char* text, size_t* first_width) {
+    DimacsDiagnostics d;
+    parse_dimacs(text, &d);
+    if (first_width) *first_width = d.first_dropped_width;
+    return d.dropped;
+}
 int ndph_scrape_header(const char* text, int* num_vars, int* num_clauses, int* num_bits, char* product, size_t cap,
                        int32_t* v1, size_t* n1, int32_t* v2, size_t* n2, size_t vcap) {
     Header h = scrape_header(text);

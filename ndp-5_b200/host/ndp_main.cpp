@@ -109,8 +109,12 @@ int main(int argc, char** argv) {
     else if (depth > 0) std::cout << "       Depth: " << depth << std::endl;
     std::cout << std::endl;
 
-    const std::vector<int32_t> clauses = parse_dimacs(text);                                        // NDP:1626
+    DimacsDiagnostics diag;
+    const std::vector<int32_t> clauses = parse_dimacs(text, &diag);                                 // NDP:1626
     if (clauses.empty()) { std::cout << "\n  Error parsing DIMACS string.\n" << std::endl; return 1; }
+    if (diag.dropped)   // the reference drops these lines without a word (NDP:639); same formula, but say so
+        std::cout << "     Warning: " << diag.dropped << " clause line(s) with a width other than 1 or 3 (first: "
+                  << diag.first_dropped_width << " literals) are ignored, as NDP 5.6.7 does.\n" << std::endl;
 
     ndp_frontier* frontier = nullptr;
     int iterations = 0, task_count = 0;

@@ -305,6 +305,13 @@ class HostLib:
         f(*args, buf, 1 << 16)
         return buf.value.decode()
 
+    def dropped(self, text):
+        """(clause lines dropped for their width, first such width) -- NDP-5_6_7.cpp:639."""
+        f = self._fn("dimacs_dropped", C.c_size_t, [C.c_char_p, C.POINTER(C.c_size_t)])
+        w = C.c_size_t(0)
+        n = f(text.encode() if isinstance(text, str) else text, C.byref(w))
+        return int(n), int(w.value)
+
     def parse(self, text):
         f = self._fn("parse_dimacs", C.c_size_t, [C.c_char_p, _i32p, C.c_size_t])
         b = text.encode() if isinstance(text, str) else text

@@ -51,6 +51,17 @@ def test_parser_and_header_match_reference(host, ref, cnf_text):
         assert h["v1"].tolist() == r["v1"].tolist() and h["v2"].tolist() == r["v2"].tolist()
 
 
+def test_parser_reports_the_widths_the_reference_drops(host, ref):
+    """NDP:639 drops clause lines of width 2 or > 3 without a word; the drop-in parses the same
+    clauses (parity) but counts what it ignored, and the program prints a warning."""
+    text = "p cnf 5 6\n1 2 3 0\n-1 2 0\n4 0\n1 2 3 4 0\n0\n-5 -4 -3 0\n"
+    got = host.parse(text)
+    assert got.tolist() == [[1, 2, 3], [0, 0, 4], [-5, -4, -3]]
+    assert got.tolist() == ref.parse(text).tolist()
+    assert host.dropped(text) == (2, 2)
+    assert host.dropped("p cnf 3 1\n1 2 3 0\n") == (0, 0)
+
+
 def test_header_known_answers(host, cnf_text):
     h = host.scrape_header(cnf_text("rsaFACT-16bit"))
     assert (h["rc"], h["num_vars"], h["num_clauses"], h["num_bits"], h["product"]) == (0, 336, 1296, 9, "35611")
