@@ -622,7 +622,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     volatile TrunkState* h_trunk = nullptr;
     TrunkState* d_trunk = nullptr;
     struct { void* p = nullptr; } trunk_mem;
-    if (use_index && !getenv("NDP_NO_TRUNK")) {
+    if (use_index && getenv("NDP_TRUNK")) {   // off by default: the windowed persistent kernel is faster from level 0
         trunk_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
         if (trunk_warps >= 2) {
             trunk_mem.p = pinned_scratch(1, sizeof(TrunkState));
@@ -1384,6 +1384,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
                   uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
     const bool use_index = engine_uses_index(f);
     int rc;
+    const double t_begin = now_ms();
+    double t_replica = 0, t_launched = 0, t_kernel_done = 0, t_results = 0;
     ndp_frontier::Replica* rep = nullptr;
     ndp_frontier::IndexReplica* irep = nullptr;
     const IndexRoot* ix = nullptr;
@@ -1391,6 +1393,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     else rc = build_replica(f, device, first, stride, &rep);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
+    t_replica = now_ms();
     const size_t n_sub = use_index ? irep->n_local : rep->n_local;   // subproblems of this shard
     if (winner) *winner = SIZE_MAX;
     if (n_sub == 0) return NDP_OK;
@@ -1524,7 +1527,9 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1, 0));
+    t_launched = now_ms();
     CUDA_TRY(cudaEventSynchronize(ev1));
+    t_kernel_done = now_ms();
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
 
@@ -1592,6 +1597,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         if (sub_v[q] == NDP_SAT && win == SIZE_MAX) { win = g; win_q = q; }
     }
     if (winner) *winner = win;
+    t_results = now_ms();
     if (win != SIZE_MAX && model) {
         // the piece (= the subproblem itself without a split) whose model is the reference's
         const unsigned long long win_piece = split.active ? (unsigned long long)h_bestp[win_q]
@@ -1639,6 +1645,10 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         // shard's own winner never parked its trail -- the job's model comes from that other shard
         if (!found) model->clear();
     }
+    if (tracing())
+        fprintf(stderr, "[ndp_dfs] dev %d: replica %.2f ms | setup+launch %.2f ms | wait %.2f ms (events %.2f ms) | results %.2f ms | "
+                        "model %.2f ms\n", device, t_replica - t_begin, t_launched - t_replica, t_kernel_done - t_launched, (double)ms,
+                t_results - t_kernel_done, now_ms() - t_results);
     if (stats) {
         stats->h2d_bytes += 8 + 4;                                   // early-exit word + work counter
         stats->d2h_bytes += d2h;
