@@ -852,7 +852,7 @@ struct IndexParams {
     int warp_bytes, off_pend;         // shared memory of one warp: state slot, then pend
 };
 
-__global__ void dfs_index_kernel(const IndexParams p) {
+__global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant__ IndexParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const IndexRoot& ix = p.ix;
     const unsigned lane = threadIdx.x & 31u;
@@ -996,7 +996,11 @@ __global__ void dfs_index_kernel(const IndexParams p) {
                 const unsigned old_piece = atomicMin(p.best_piece + o, q);
                 const unsigned long long old = atomicMin(p.best, g);
                 if (g < old)
-                    for (int d = 0; d < p.n_peers; ++d) atomicMin_system(p.peer_best[d], g);
+                    {
+#pragma unroll
+                        for (int d = 0; d < 8; ++d)   // constant indices: the parameter block stays in constant memory
+                            if (d < p.n_peers) atomicMin_system(p.peer_best[d], g);
+                    }
                 park = q < old_piece && g <= old;
             }
             park = __shfl_sync(kFullMask, park, 0);

@@ -178,7 +178,7 @@ struct DfsParams {
 };
 
 template <bool kSmemW>
-__global__ void dfs_kernel(const DfsParams p) {
+__global__ void dfs_kernel(const __grid_constant__ DfsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = threadIdx.x >> 5;
@@ -292,7 +292,11 @@ __global__ void dfs_kernel(const DfsParams p) {
             if (lane == 0) {
                 old = atomicMin(p.best, g);
                 if (g < old)
-                    for (int d = 0; d < p.n_peers; ++d) atomicMin_system(p.peer_best[d], g);
+                    {
+#pragma unroll
+                        for (int d = 0; d < 8; ++d)   // constant indices: the parameter block stays in constant memory
+                            if (d < p.n_peers) atomicMin_system(p.peer_best[d], g);
+                    }
             }
             old = __shfl_sync(kFullMask, old, 0);
             if (g < old) {  // this warp now holds the lowest-index model: park it in its slot

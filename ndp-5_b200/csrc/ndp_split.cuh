@@ -214,7 +214,7 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
     }
 }
 
-__global__ void __launch_bounds__(1024) dfs_split_kernel(const SplitParams p) {
+__global__ void __launch_bounds__(1024) dfs_split_kernel(const __grid_constant__ SplitParams p) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char split_smem[];
