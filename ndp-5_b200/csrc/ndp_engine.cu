@@ -158,6 +158,7 @@ struct ndp_frontier {
         IndexRoot ix;
     };
     std::vector<RootIndex> root_indexes;
+    size_t root_borrowed = 0;               // the first root_borrowed entries belong to another frontier (piece frontiers)
     // ---- stats
     uint64_t bfs_evals = 0, bfs_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     double bfs_kernel_ms = 0;
@@ -223,7 +224,8 @@ struct ndp_frontier {
             if (r.d_slot_ptr) dev_free((void*)r.d_slot_ptr);
             if (r.d_meta) dev_free(r.d_meta);
         }
-        for (auto& r : root_indexes) {
+        for (size_t i = root_borrowed; i < root_indexes.size(); ++i) {
+            RootIndex& r = root_indexes[i];
             cudaSetDevice(r.device);
             if (r.d_root) dev_free(r.d_root);
             if (r.d_occ_off) dev_free(r.d_occ_off);
@@ -1207,14 +1209,28 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
     if (f->states) {
         // the BFS already produced state slots: use them in place (home device) or copy the shard over
         if (device != f->device && r.n_local) {
-            CUDA_TRY(dev_alloc(&r.own_slots, r.n_local * (size_t)ix.slot_words * 4));
+            // gather the shard's slots into one buffer on the home device, then ONE peer copy
+            const size_t bytes = r.n_local * (size_t)ix.slot_words * 4;
+            CUDA_TRY(dev_alloc(&r.own_slots, bytes));
+            std::vector<const unsigned*> src(r.n_local);
             for (size_t q = 0; q < r.n_local; ++q) {
                 const Entry& e = f->entries[first + q * stride];
-                CUDA_TRY(cudaMemcpyPeerAsync(r.own_slots + q * ix.slot_words, device,
-                                             f->sbuf[e.buf] + (size_t)e.slot * ix.slot_words, f->device,
-                                             (size_t)ix.slot_words * 4, 0));
+                src[q] = f->sbuf[e.buf] + (size_t)e.slot * ix.slot_words;
             }
-            CUDA_TRY(cudaStreamSynchronize(0));
+            CUDA_TRY(cudaSetDevice(f->device));
+            DevBuf d_src, d_stage;
+            CUDA_TRY(dev_alloc(&d_src.p, r.n_local * sizeof(unsigned*)));
+            CUDA_TRY(dev_alloc(&d_stage.p, bytes));
+            CUDA_TRY(cudaMemcpy(d_src.p, src.data(), r.n_local * sizeof(unsigned*), cudaMemcpyHostToDevice));
+            slot_gather_kernel<<<(int)std::min<size_t>((r.n_local + 3) / 4, (size_t)148 * 16), 128>>>(
+                d_src.as<const unsigned*>(), (int)r.n_local, ix.slot_words, d_stage.as<unsigned>());
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyPeer(r.own_slots, device, d_stage.p, f->device, bytes));
+            CUDA_TRY(cudaDeviceSynchronize());
+            dev_free(d_src.p); d_src.p = nullptr;      // freed on the device that owns them
+            dev_free(d_stage.p); d_stage.p = nullptr;
+            CUDA_TRY(cudaSetDevice(device));
+            f->h2d_bytes += r.n_local * sizeof(unsigned*);
         }
         for (size_t q = 0; q < r.n_local; ++q) {
             const Entry& e = f->entries[first + q * stride];
@@ -1661,44 +1677,10 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     return NDP_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, size_t* exit_flag,
-                  uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
-                  uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
-    if (!f) return fail(NDP_E_INVALID, "frontier is null");
-    if (stride == 0) return fail(NDP_E_INVALID, "stride must be >= 1");
-    int rc = check_device();
-    if (rc) return rc;
-    if (stats) memset(stats, 0, sizeof *stats);
-    if (model_len) *model_len = 0;
-    unsigned long long best_init = ~0ull;
-    if (exit_flag && *exit_flag != SIZE_MAX) best_init = *exit_flag;
-    std::vector<int32_t> m;
-    size_t win = SIZE_MAX;
-    rc = dfs_on_device(f, f->device, first, stride, early_exit, nullptr, nullptr, 0, best_init, verdict, &win,
-                       &m, nodes, evals, stats);
-    if (rc) return rc;
-    if (winner) *winner = win;
-    if (win != SIZE_MAX) {
-        if (exit_flag && (*exit_flag == SIZE_MAX || win < *exit_flag)) *exit_flag = win;
-        if (model_len) *model_len = m.size();
-        if (model) {
-            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
-            memcpy(model, m.data(), m.size() * sizeof(int32_t));
-        }
-    }
-    return NDP_OK;
-}
-
-int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
-                  int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats) {
-    if (!f) return fail(NDP_E_INVALID, "frontier is null");
-    if (n_gpus <= 1)
-        return ndp_dfs_shard(f, 0, 1, early_exit, nullptr, verdict, winner, model, model_cap, model_len, nullptr,
-                             nullptr, stats);
+// The frontier on n_gpus devices of this process: static interleaved split k -> k mod n_gpus, one host
+// thread per device, peer-visible early-exit words.  nodes / evals (may be null): per-element counters.
+int batch_core(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner, int32_t* model,
+               size_t model_cap, size_t* model_len, uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
     int have = 0;
     int rc = ndp_device_count(&have);
     if (rc) return rc;
@@ -1747,7 +1729,7 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         th.emplace_back([&, i]() {
             memset(&st[i], 0, sizeof(ndp_stats));
             rcs[i] = dfs_on_device(f, devs[i], (size_t)i, (size_t)n_gpus, early_exit, best[i], best.data(), n_gpus,
-                                   none, verdict, &wins[i], &models[i], nullptr, nullptr, &st[i]);
+                                   none, verdict, &wins[i], &models[i], nodes, evals, &st[i]);
             if (rcs[i]) errs[i] = g_err;
         });
     for (auto& t : th) t.join();
@@ -1774,6 +1756,197 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         }
     }
     return NDP_OK;
+}
+
+
+// Pieces of a split as a frontier of their own: element p = piece p (state slots in the split's arena,
+// no choices), so that batch_core can shard them over devices like subproblems.  Per-piece results are
+// then folded back per subproblem exactly as in dfs_on_device.
+int batch_over_pieces(ndp_frontier* f, const IndexRoot& ix, SplitRun& split, int n_gpus, int early_exit,
+                      uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                      ndp_stats* stats) {
+    const size_t n_sub = f->entries.size(), np = split.n_pieces;
+    const SplitLevel& L = split.sp.lv[split.side];
+    if (winner) *winner = SIZE_MAX;
+    if (model_len) *model_len = 0;
+    std::vector<const unsigned*> h_ptr(std::max(np, (size_t)1));
+    std::vector<BfsNode> h_meta(std::max(np, (size_t)1));
+    std::vector<int32_t> h_orig(std::max(np, (size_t)1));
+    std::vector<unsigned long long> h_pre_n(std::max(np, (size_t)1)), h_pre_e(std::max(np, (size_t)1)), h_tail_n(n_sub), h_tail_e(n_sub);
+    CUDA_TRY(cudaSetDevice(f->device));
+    if (np) {
+        CUDA_TRY(cudaMemcpy(h_ptr.data(), L.ptr, np * sizeof(unsigned*), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_meta.data(), L.meta, np * sizeof(BfsNode), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_orig.data(), L.orig, np * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_pre_n.data(), L.pre_nodes, np * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_pre_e.data(), L.pre_evals, np * 8, cudaMemcpyDeviceToHost));
+    }
+    CUDA_TRY(cudaMemcpy(h_tail_n.data(), split.sp.tail_nodes, n_sub * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h_tail_e.data(), split.sp.tail_evals, n_sub * 8, cudaMemcpyDeviceToHost));
+    // every surviving piece of the last level sits in the arena that level wrote (LEAF pieces have no slot)
+    unsigned* arena = split.sp.sbuf[split.side];
+    std::unique_ptr<ndp_frontier> pf(new ndp_frontier);
+    pf->device = f->device;
+    pf->max_var = f->max_var;
+    pf->states = true;
+    pf->has_root = true;
+    pf->root_c3 = f->root_c3;
+    pf->root_indexes = f->root_indexes;      // same root: share the per-device indexes already built ...
+    pf->root_borrowed = pf->root_indexes.size();
+    pf->host_tree_ready = true;
+    pf->sbuf[0] = arena;
+    pf->scap_slots[0] = 0;
+    for (size_t pc = 0; pc < np; ++pc) {
+        uint32_t slot = 0;
+        if (h_ptr[pc]) {
+            const size_t off = (size_t)(h_ptr[pc] - arena);
+            if (h_ptr[pc] < arena || off % (size_t)ix.slot_words) { pf->sbuf[0] = nullptr; return fail(NDP_E_CUDA, "piece slot outside the split arena"); }
+            slot = (uint32_t)(off / (size_t)ix.slot_words);
+        }
+        pf->entries.push_back(Entry{0, slot, h_meta[pc].n, -1, h_meta[pc].kind, h_meta[pc].lit});
+    }
+    std::vector<uint8_t> pv(std::max(np, (size_t)1), NDP_NOT_RUN);
+    std::vector<uint64_t> pn(std::max(np, (size_t)1), 0), pe(std::max(np, (size_t)1), 0);
+    std::vector<int32_t> tail(model_cap ? model_cap : 1);
+    size_t pwin = SIZE_MAX, tail_len = 0;
+    ndp_stats st;
+    memset(&st, 0, sizeof st);
+    int rc = NDP_OK;
+    if (np) rc = batch_core(pf.get(), n_gpus, early_exit, pv.data(), &pwin, tail.data(), tail.size(), &tail_len, pn.data(),
+                            pe.data(), &st);
+    pf->sbuf[0] = nullptr;   // the arena belongs to the split
+    for (size_t i = pf->root_borrowed; i < pf->root_indexes.size(); ++i)   // ... and keep the ones built for new devices
+        f->root_indexes.push_back(pf->root_indexes[i]);
+    pf->root_borrowed = pf->root_indexes.size();
+    pf.reset();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(f->device));
+    // fold the pieces back: first piece with a model decides the subproblem; counters as in dfs_on_device
+    std::vector<size_t> first_sat(n_sub, SIZE_MAX);
+    for (size_t pc = 0; pc < np; ++pc)
+        if (pv[pc] == NDP_SAT && first_sat[(size_t)h_orig[pc]] == SIZE_MAX) first_sat[(size_t)h_orig[pc]] = pc;
+    std::vector<uint8_t> sub_v(n_sub, NDP_UNSAT);
+    std::vector<unsigned long long> sub_n(n_sub, 0), sub_e(n_sub, 0);
+    for (size_t pc = 0; pc < np; ++pc) {
+        const size_t o = (size_t)h_orig[pc];
+        if (first_sat[o] != SIZE_MAX && pc > first_sat[o]) continue;
+        sub_n[o] += h_pre_n[pc] + pn[pc];
+        sub_e[o] += h_pre_e[pc] + pe[pc];
+        if (pv[pc] == NDP_NOT_RUN && sub_v[o] == NDP_UNSAT) sub_v[o] = NDP_NOT_RUN;
+    }
+    size_t win = SIZE_MAX;
+    uint64_t tn = 0, te = 0;
+    for (size_t o = 0; o < n_sub; ++o) {
+        if (first_sat[o] != SIZE_MAX) sub_v[o] = NDP_SAT;
+        else if (sub_v[o] == NDP_UNSAT) { sub_n[o] += h_tail_n[o]; sub_e[o] += h_tail_e[o]; }
+        if (verdict) verdict[o] = sub_v[o];
+        tn += sub_n[o]; te += sub_e[o];
+        if (sub_v[o] == NDP_SAT && win == SIZE_MAX) win = o;
+    }
+    if (winner) *winner = win;
+    if (win != SIZE_MAX && pwin != first_sat[win])
+        return fail(NDP_E_CUDA, "piece winner disagrees with the per-subproblem fold");
+    if (win != SIZE_MAX && (model || model_len)) {
+        // choices_k ++ the split's path to the winning piece ++ what the device that searched it appended
+        std::vector<int32_t> m;
+        if ((rc = frontier_choices(f, win, m))) return rc;
+        CUDA_TRY(cudaSetDevice(f->device));
+        const int cap = std::max(f->max_var, 1) + 8;
+        int32_t leaf = -1, start = 0;
+        CUDA_TRY(cudaMemcpy(&leaf, L.tnode + pwin, 4, cudaMemcpyDeviceToHost));
+        DevBuf d_out, d_start;
+        CUDA_TRY(dev_alloc(&d_out.p, (size_t)cap * 4));
+        CUDA_TRY(dev_alloc(&d_start.p, 4));
+        split_path_kernel<<<1, 1>>>(split.sp.t_parent, split.sp.t_lit, split.sp.t_seg_off, split.sp.t_seg_len, split.sp.log,
+                                    leaf, d_out.as<int32_t>(), cap, d_start.as<int32_t>());
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(&start, d_start.p, 4, cudaMemcpyDeviceToHost));
+        if (start < 0) return fail(NDP_E_CUDA, "split path longer than the variable count");
+        std::vector<int32_t> path((size_t)(cap - start));
+        if (!path.empty())
+            CUDA_TRY(cudaMemcpy(path.data(), d_out.as<int32_t>() + start, path.size() * 4, cudaMemcpyDeviceToHost));
+        m.insert(m.end(), path.begin(), path.end());
+        m.insert(m.end(), tail.begin(), tail.begin() + tail_len);
+        if (model_len) *model_len = m.size();
+        if (model) {
+            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, m.data(), m.size() * sizeof(int32_t));
+        }
+    }
+    if (stats) {
+        stats->nodes += tn;
+        stats->clause_evals += te;
+        stats->rebuilds += st.rebuilds;
+        stats->kernel_ms += st.kernel_ms;
+        stats->launches += st.launches;
+        stats->h2d_bytes += st.h2d_bytes;
+        stats->d2h_bytes += st.d2h_bytes + np * (8 + 16 + 4 + 16) + n_sub * 16;
+    }
+    return NDP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, size_t* exit_flag,
+                  uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                  uint64_t* nodes, uint64_t* evals, ndp_stats* stats) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (stride == 0) return fail(NDP_E_INVALID, "stride must be >= 1");
+    int rc = check_device();
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (model_len) *model_len = 0;
+    unsigned long long best_init = ~0ull;
+    if (exit_flag && *exit_flag != SIZE_MAX) best_init = *exit_flag;
+    std::vector<int32_t> m;
+    size_t win = SIZE_MAX;
+    rc = dfs_on_device(f, f->device, first, stride, early_exit, nullptr, nullptr, 0, best_init, verdict, &win,
+                       &m, nodes, evals, stats);
+    if (rc) return rc;
+    if (winner) *winner = win;
+    if (win != SIZE_MAX) {
+        if (exit_flag && (*exit_flag == SIZE_MAX || win < *exit_flag)) *exit_flag = win;
+        if (model_len) *model_len = m.size();
+        if (model) {
+            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, m.data(), m.size() * sizeof(int32_t));
+        }
+    }
+    return NDP_OK;
+}
+
+int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
+                  int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (n_gpus <= 1)
+        return ndp_dfs_shard(f, 0, 1, early_exit, nullptr, verdict, winner, model, model_cap, model_len, nullptr,
+                             nullptr, stats);
+    int rc = check_device();
+    if (rc) return rc;
+    // A frontier too narrow for n_gpus devices is first cut into DFS-order pieces on its home device;
+    // the PIECES are then what the devices share out (each may cut its own pieces further).
+    if (engine_uses_index(f) && !f->entries.empty()) {
+        const IndexRoot* ix = nullptr;
+        ndp_frontier::IndexReplica* rep = nullptr;
+        if ((rc = build_index_replica(f, f->device, 0, 1, &ix, &rep))) return rc;
+        CUDA_TRY(cudaSetDevice(f->device));
+        IndexLaunchPlan iplan;
+        if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
+        const int n_warps = iplan.grid * iplan.warps_per_cta;
+        const size_t target = split_target(f->entries.size(), n_warps * n_gpus);
+        if (target > f->entries.size()) {
+            if (stats) memset(stats, 0, sizeof *stats);
+            SplitRun split;
+            const double t_split = now_ms();
+            if ((rc = run_split(f->device, *ix, *rep, target, split, stats))) return rc;
+            if (stats) stats->kernel_ms += now_ms() - t_split;   // run_split returns after the kernel (it reads its state back)
+            if (split.active) return batch_over_pieces(f, *ix, split, n_gpus, early_exit, verdict, winner, model, model_cap,
+                                                       model_len, stats);
+        }
+    }
+    return batch_core(f, n_gpus, early_exit, verdict, winner, model, model_cap, model_len, nullptr, nullptr, stats);
 }
 
 }  // extern "C"

@@ -1038,6 +1038,15 @@ __global__ void prefix_table_kernel(const int32_t* __restrict__ entry_tree, cons
     }
 }
 
+// Gather scattered state slots into a dense buffer (slot q <- ptr[q]); one warp per slot.
+__global__ void __launch_bounds__(128) slot_gather_kernel(const unsigned* const* __restrict__ ptr, int count,
+                                                          int slot_words, unsigned* __restrict__ dst) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block)
+        slot_copy(dst + (size_t)q * slot_words, ptr[q], slot_words, lane);
+}
+
 // One thread: the choices of one subproblem, leaf to root (the host reverses them).
 __global__ void tree_path_kernel(const int32_t* __restrict__ tree_parent, const int32_t* __restrict__ tree_lit,
                                  int32_t leaf, int32_t* __restrict__ out, int cap, int32_t* __restrict__ out_len) {
