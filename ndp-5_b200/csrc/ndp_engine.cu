@@ -1296,14 +1296,19 @@ struct SplitRun {
 };
 
 // How many pieces the shard should be cut into (0 = leave the subproblems whole).
-size_t split_target(size_t n_sub, int n_warps) {
+// per_warp: pieces per resident warp the automatic policy aims for.  Two keep the device busy; searches
+// that run for seconds have heavy-tailed piece sizes, and a split level costs about a millisecond, so
+// large CNFs (whose subtrees are deep) are cut finer: the tail is what bounds an early-exit run.
+size_t split_target(size_t n_sub, int n_warps, int n_root_clauses) {
     long long mode = g_split;
     if (mode < 0)
         if (const char* e = getenv("NDP_SPLIT")) mode = !strcmp(e, "off") ? 0 : atoll(e);
     if (mode == 0 || n_sub == 0) return 0;
     if (mode > 0) return (size_t)mode > n_sub ? (size_t)mode : 0;
+    size_t per_warp = n_root_clauses > 16384 ? 32 : n_root_clauses > 8192 ? 8 : 2;
+    if (const char* e = getenv("NDP_SPLIT_PER_WARP")) per_warp = (size_t)std::max(1, atoi(e));
     // auto: only shards that cannot occupy the device (fewer than two subproblems per resident warp)
-    return n_sub < (size_t)2 * n_warps ? (size_t)2 * n_warps : 0;
+    return n_sub < (size_t)2 * n_warps ? per_warp * (size_t)n_warps : 0;
 }
 
 int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
@@ -1331,7 +1336,7 @@ int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica&
     if (per_sm < 1) return NDP_OK;
     const size_t cap = 2 * (size_t)sp.target;                 // pieces per level (children of a level: <= cap)
     const size_t cap_tree = n_sub + 24 * cap;
-    const size_t cap_log = std::max<size_t>((size_t)16 << 20, 4 * cap * (size_t)sp.chain_cap / 8);
+    const size_t cap_log = std::max<size_t>((size_t)32 << 20, cap * (size_t)sp.chain_cap);   // shorts; a level needs m * chain_cap free
     const size_t slot_bytes = (size_t)ix.slot_words * 4;
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(dev_alloc(&run.ptr[b].p, cap * sizeof(unsigned*)));
@@ -1438,7 +1443,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     // index engine: a shard too narrow for the device is first cut into pieces in DFS order
     SplitRun split;
     if (use_index) {
-        const size_t target = split_target(n_sub, n_warps);
+        const size_t target = split_target(n_sub, n_warps, ix->n_root);
         if (target > n_sub && (rc = run_split(device, *ix, *irep, target, split, stats))) return rc;
     }
     const size_t nl = split.active ? split.n_pieces : n_sub;         // units the DFS kernel pulls
@@ -1935,7 +1940,7 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
         const int n_warps = iplan.grid * iplan.warps_per_cta;
-        const size_t target = split_target(f->entries.size(), n_warps * n_gpus);
+        const size_t target = split_target(f->entries.size(), n_warps * n_gpus, ix->n_root);
         if (target > f->entries.size()) {
             if (stats) memset(stats, 0, sizeof *stats);
             SplitRun split;
