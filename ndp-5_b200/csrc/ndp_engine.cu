@@ -1296,9 +1296,11 @@ struct SplitRun {
 };
 
 // How many pieces the shard should be cut into (0 = leave the subproblems whole).
-// per_warp: pieces per resident warp the automatic policy aims for.  Two keep the device busy; searches
-// that run for seconds have heavy-tailed piece sizes, and a split level costs about a millisecond, so
-// large CNFs (whose subtrees are deep) are cut finer: the tail is what bounds an early-exit run.
+// Automatic policy: a shard with fewer units than per_warp pieces per resident warp is cut into that many.
+// Two per warp keep the device busy; searches that run for seconds have heavy-tailed piece sizes and a
+// split level costs about a millisecond, so large CNFs (whose subtrees are deep) are cut finer -- the
+// tail is what bounds an early-exit run.  n_root_clauses = 0: the coarse cut used to share a narrow
+// frontier out over several devices (each device then refines its share).
 size_t split_target(size_t n_sub, int n_warps, int n_root_clauses) {
     long long mode = g_split;
     if (mode < 0)
@@ -1306,9 +1308,9 @@ size_t split_target(size_t n_sub, int n_warps, int n_root_clauses) {
     if (mode == 0 || n_sub == 0) return 0;
     if (mode > 0) return (size_t)mode > n_sub ? (size_t)mode : 0;
     size_t per_warp = n_root_clauses > 16384 ? 32 : n_root_clauses > 8192 ? 8 : 2;
-    if (const char* e = getenv("NDP_SPLIT_PER_WARP")) per_warp = (size_t)std::max(1, atoi(e));
-    // auto: only shards that cannot occupy the device (fewer than two subproblems per resident warp)
-    return n_sub < (size_t)2 * n_warps ? per_warp * (size_t)n_warps : 0;
+    if (n_root_clauses > 0)
+        if (const char* e = getenv("NDP_SPLIT_PER_WARP")) per_warp = (size_t)std::max(1, atoi(e));
+    return n_sub < per_warp * (size_t)n_warps ? per_warp * (size_t)n_warps : 0;
 }
 
 int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
@@ -1940,7 +1942,7 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
         const int n_warps = iplan.grid * iplan.warps_per_cta;
-        const size_t target = split_target(f->entries.size(), n_warps * n_gpus, ix->n_root);
+        const size_t target = split_target(f->entries.size(), n_warps * n_gpus, 0);
         if (target > f->entries.size()) {
             if (stats) memset(stats, 0, sizeof *stats);
             SplitRun split;
