@@ -109,6 +109,15 @@ int ndp_frontier_dims(const ndp_frontier* f, size_t k, size_t* n_clauses, size_t
 int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets, const int32_t* choices,
                            const size_t* choice_offsets, size_t count, ndp_frontier** out);
 
+/* Tell a frontier built by ndp_frontier_from_host which clause array it was granulated from (the
+ * DIMACS file the reference still requires on -r, NDP:1584-1626).  The library checks, on the device,
+ * that every element really is that root filtered by its choices (the equivalence ResolutionStep
+ * guarantees, NDP:700-750) and then searches the frontier with the occurrence-index engine -- the same
+ * speed and the same piece split as a frontier that came straight from ndp_bfs.  If the check fails
+ * (another file, edited JSON) NDP_E_INVALID is returned, the frontier is left as it was and is searched
+ * by the clause-streaming engine on exactly the clause sets it holds, as the reference does. */
+int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_clauses);
+
 void ndp_frontier_free(ndp_frontier* f);
 
 /* ---- DFS over the frontier --------------------------------------------------------------

@@ -1052,6 +1052,116 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
     return NDP_OK;
 }
 
+int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_clauses) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (f->has_root) return NDP_OK;                                   // BFS-born: nothing to do
+    if (!clauses3 && n_clauses) return fail(NDP_E_INVALID, "clauses3 is null");
+    if (n_clauses > (size_t)INT_MAX / 4) return fail(NDP_E_UNSUPPORTED, "too many clauses");
+    int rc = check_device();
+    if (rc) return rc;
+    if (f->device != g_device) return fail(NDP_E_INVALID, "frontier lives on another device");
+    const size_t count = f->entries.size();
+    if (count == 0 || count > (size_t)INT_MAX) return NDP_OK;
+    // candidate root: everything below is undone if the frontier turns out not to descend from it
+    std::vector<pclause> packed(std::max(n_clauses, (size_t)1));
+    int max_var = f->max_var;
+    if (!pack_host(clauses3, n_clauses, packed.data(), max_var))
+        return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
+    const int old_max_var = f->max_var;
+    f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
+    f->has_root = true;
+    f->max_var = max_var;
+    auto undo = [&](int code, const std::string& msg) {
+        for (auto& r : f->root_indexes) {
+            if (r.d_root) dev_free(r.d_root);
+            if (r.d_occ_off) dev_free(r.d_occ_off);
+            if (r.d_occ) dev_free(r.d_occ);
+        }
+        f->root_indexes.clear();
+        if (f->sbuf[0]) { dev_free(f->sbuf[0]); f->sbuf[0] = nullptr; f->scap_slots[0] = 0; }
+        f->root_c3.clear();
+        f->has_root = false;
+        f->states = false;
+        f->max_var = old_max_var;
+        return fail(code, msg);
+    };
+#define ATT_TRY(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return undo(NDP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    const IndexRoot* ix = nullptr;
+    if ((rc = get_root_index(f, f->device, &ix))) return undo(rc, g_err);
+    const size_t slot_bytes = (size_t)ix->slot_words * 4;
+    if (8 * slot_bytes > 227 * 1024) return undo(NDP_E_UNSUPPORTED, "root too large for the index engine's state slots");
+    // 1. assignment table of every element from its choices, 2. state slots from the tables
+    const size_t tw = (size_t)ix->table_words;
+    std::vector<unsigned> tables(count * tw, 0u);
+    for (size_t k = 0; k < count; ++k)
+        for (size_t i = f->flat_off[k]; i < f->flat_off[k + 1]; ++i) {
+            const int l = f->flat_choices[i];
+            const unsigned v = (unsigned)std::abs(l);
+            if (l == 0 || v > (unsigned)max_var) return undo(NDP_E_INVALID, "a choice names a variable the root does not have");
+            tables[k * tw + (v >> 4)] |= (l > 0 ? 1u : 2u) << ((v & 15u) * 2u);
+        }
+    DevBuf d_tables, d_meta, d_scratch, d_n, d_expect, d_flag, d_ptr;
+    cudaError_t ce;
+    if ((ce = dev_alloc(&d_tables.p, std::max(tables.size(), (size_t)1) * 4)) != cudaSuccess ||
+        (ce = dev_alloc(&d_meta.p, count * sizeof(BfsNode))) != cudaSuccess ||
+        (ce = dev_alloc(&f->sbuf[0], count * slot_bytes)) != cudaSuccess)
+        return undo(NDP_E_NOMEM, cudaGetErrorString(ce));
+    f->scap_slots[0] = count;
+    ATT_TRY(cudaMemcpy(d_tables.p, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice));
+    f->h2d_bytes += tables.size() * 4;
+    ATT_TRY(cudaFuncSetAttribute(index_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * slot_bytes)));
+    {
+        const int wpb = 4;
+        const int grid = (int)std::min<size_t>((count + wpb - 1) / wpb, (size_t)148 * 16);
+        index_states_kernel<<<grid, wpb * 32, wpb * slot_bytes>>>(*ix, d_tables.as<unsigned>(), f->sbuf[0], (int)count,
+                                                                  d_meta.as<BfsNode>());
+        ATT_TRY(cudaGetLastError());
+    }
+    // 3. the proof: root filtered by each element's table must reproduce the element's clause list
+    std::vector<int32_t> expect(count);
+    for (size_t k = 0; k < count; ++k) expect[k] = f->entries[k].n;
+    const size_t sstride = (size_t)pad_up((int)n_clauses + 1);
+    const size_t chunk = std::max<size_t>(1, std::min(count, ((size_t)256 << 20) / (sstride * sizeof(pclause))));
+    if ((ce = dev_alloc(&d_scratch.p, chunk * sstride * sizeof(pclause))) != cudaSuccess ||
+        (ce = dev_alloc(&d_n.p, chunk * 4)) != cudaSuccess || (ce = dev_alloc(&d_expect.p, count * 4)) != cudaSuccess ||
+        (ce = dev_alloc(&d_flag.p, 4)) != cudaSuccess || (ce = dev_alloc(&d_ptr.p, chunk * sizeof(unsigned*))) != cudaSuccess)
+        return undo(NDP_E_NOMEM, cudaGetErrorString(ce));
+    ATT_TRY(cudaMemcpy(d_expect.p, expect.data(), count * 4, cudaMemcpyHostToDevice));
+    ATT_TRY(cudaMemset(d_flag.p, 0, 4));
+    std::vector<const unsigned*> ptrs(chunk);
+    for (size_t k0 = 0; k0 < count; k0 += chunk) {
+        const size_t c = std::min(chunk, count - k0);
+        for (size_t i = 0; i < c; ++i) ptrs[i] = f->sbuf[0] + (k0 + i) * (size_t)ix->slot_words;
+        ATT_TRY(cudaMemcpy(d_ptr.p, ptrs.data(), c * sizeof(unsigned*), cudaMemcpyHostToDevice));
+        const int grid = (int)std::min<size_t>((c + 3) / 4, (size_t)148 * 16);
+        index_materialise_kernel<<<grid, 128>>>(*ix, d_ptr.as<const unsigned*>(), (int)c, d_scratch.as<pclause>(), sstride,
+                                                d_n.as<int32_t>());
+        clause_lists_equal_kernel<<<grid, 128>>>(d_scratch.as<pclause>(), sstride, d_n.as<int32_t>(),
+                                                 f->buf[0] + k0 * f->stride, f->stride, d_expect.as<int32_t>() + k0, (int)c,
+                                                 d_flag.as<unsigned>());
+        ATT_TRY(cudaGetLastError());
+    }
+    unsigned mismatch = 0;
+    ATT_TRY(cudaMemcpy(&mismatch, d_flag.p, 4, cudaMemcpyDeviceToHost));
+    if (mismatch) return undo(NDP_E_INVALID, "the frontier is not this root filtered by its choices (different DIMACS file?)");
+    std::vector<BfsNode> meta(count);
+    ATT_TRY(cudaMemcpy(meta.data(), d_meta.p, count * sizeof(BfsNode), cudaMemcpyDeviceToHost));
+    f->d2h_bytes += count * sizeof(BfsNode) + 4;
+    for (size_t k = 0; k < count; ++k) {
+        Entry& e = f->entries[k];
+        e.buf = 0; e.slot = (uint32_t)k; e.kind = meta[k].kind; e.lit = meta[k].lit;   // e.n and the clause lists stay as loaded
+    }
+    f->states = true;
+    f->materialised = true;   // buf[0] slot k already holds element k's clause list
+    f->replicas.clear();      // (none built yet for a fresh frontier; scan replicas would still be valid)
+    return NDP_OK;
+#undef ATT_TRY
+}
+
 void ndp_frontier_free(ndp_frontier* f) { delete f; }
 
 }  // extern "C"

@@ -814,6 +814,32 @@ __global__ void __launch_bounds__(128) index_materialise_kernel(const IndexRoot 
     }
 }
 
+// Does list a[q] (n[q] records at a + q * stride_a) equal list b[q]?  One warp per element; any difference
+// (a length that is not expect_n[q] included) raises *mismatch.  Used to check that a resumed frontier
+// really is "the root filtered by its choices" before it is handed to the index engine.
+__global__ void __launch_bounds__(128) clause_lists_equal_kernel(const pclause* __restrict__ a, size_t stride_a,
+                                                                 const int32_t* __restrict__ n_a,
+                                                                 const pclause* __restrict__ b, size_t stride_b,
+                                                                 const int32_t* __restrict__ expect_n, int count,
+                                                                 unsigned* __restrict__ mismatch) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block) {
+        const int n = n_a[q];
+        bool bad = n != expect_n[q];
+        if (!bad) {
+            const pclause* pa = a + (size_t)q * stride_a;
+            const pclause* pb = b + (size_t)q * stride_b;
+            for (int i = lane; i < n; i += 32) {
+                const pclause x = pa[i], y = pb[i];
+                // literal codes only: the cached zero count is derived data
+                bad |= x.x != y.x || (x.y & 0xffffu) != (y.y & 0xffffu);
+            }
+        }
+        if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(mismatch, 1u);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // DFS over state slots.  Persistent grid; a warp pulls the next subproblem of its shard, copies its
 // state slot into shared memory and runs the whole search there.  The explicit stack is the trail

@@ -130,6 +130,10 @@ int main(int argc, char** argv) {
         if (ndp_frontier_from_host(j.clauses3.data(), j.clause_off.data(), j.choices.data(), j.choice_off.data(),
                                    j.count(), &frontier) != NDP_OK)
             return die("loading the BFS results onto the GPU");
+        // the DIMACS file is the root this frontier was granulated from (NDP:1584-1626): once the library has
+        // checked that, the resumed run is searched exactly like a straight one
+        if (ndp_frontier_attach_root(frontier, clauses.data(), clauses.size() / 3) != NDP_OK)
+            std::cout << "\n        Note: " << ndp_last_error() << " -- searching the loaded clause sets as they are.\n";
         bfs_seconds = j.bfs_time;
         char b[64];
         snprintf(b, sizeof b, "%.2f", bfs_seconds);

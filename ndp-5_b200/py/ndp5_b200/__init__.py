@@ -59,6 +59,7 @@ def _load():
         "ndp_frontier_get": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(_i32p), _szp, C.POINTER(_i32p), _szp]),
         "ndp_frontier_dims": (C.c_int, [C.c_void_p, C.c_size_t, _szp, _szp]),
         "ndp_frontier_from_host": (C.c_int, [_i32p, _szp, _i32p, _szp, C.c_size_t, C.POINTER(C.c_void_p)]),
+        "ndp_frontier_attach_root": (C.c_int, [C.c_void_p, _i32p, C.c_size_t]),
         "ndp_frontier_free": (None, [C.c_void_p]),
         "ndp_dfs_shard": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, _szp, _u8p, _szp, _i32p,
                                     C.c_size_t, _szp, _u64p, _u64p, C.POINTER(Stats)]),
@@ -171,6 +172,16 @@ class Frontier:
                                  C.byref(st)))
         return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
                     model=model[:mlen.value].copy(), stats=st.as_dict())
+
+    def attach_root(self, clauses):
+        """ndp_frontier_attach_root: True if the resumed frontier descends from this clause array (index engine
+        from here on), False if the library refused (NDP_E_INVALID) and left the frontier as it was."""
+        a = np.ascontiguousarray(np.asarray(clauses, dtype=np.int32).reshape(-1, 3))
+        rc = lib.ndp_frontier_attach_root(self.h, a.ctypes.data_as(_i32p), a.shape[0])
+        if rc == NDP_E_INVALID:
+            return False
+        _check(rc)
+        return True
 
     def free(self):
         if self.h:

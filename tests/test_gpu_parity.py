@@ -219,6 +219,45 @@ def test_resume_equals_straight_run(nd, oracle, cnf_text):
         fr2.free()
 
 
+def test_resume_with_root_uses_the_index_engine(nd, oracle, cnf_text):
+    """-r with the DIMACS root attached (ndp_frontier_attach_root): the library proves on the device
+    that the loaded frontier is the root filtered by its choices, then searches it like a straight
+    run -- same verdicts, counters and model.  A foreign root, a tampered clause or a tampered choice
+    is refused and the frontier stays searchable as loaded."""
+    for name, q in [("prime-16bit", 64), ("rsaFACT-16bit", 32), ("rsaFACT-24bit", 100)]:
+        A = oracle.parse(cnf_text(name))
+        fr = nd.bfs(A, 0, True, q)
+        r1 = fr.dfs_shard()
+        items = gpu_frontier_list(fr)
+        fr2 = nd.frontier_from_host(items)
+        assert fr2.attach_root(A) is True
+        assert fr2.attach_root(A) is True          # idempotent
+        for k in (0, len(items) - 1):
+            c2, h2 = fr2.get(k)
+            assert (c2 == items[k][0]).all() and (h2 == items[k][1]).all()
+        r2 = fr2.dfs_shard()
+        assert r1["verdict"].tolist() == r2["verdict"].tolist()
+        assert r1["nodes"].tolist() == r2["nodes"].tolist() and r1["evals"].tolist() == r2["evals"].tolist()
+        assert r1["winner"] == r2["winner"] and r1["model"].tolist() == r2["model"].tolist()
+        # refused: another CNF of the same shape, a flipped literal in one clause list, a flipped choice
+        other = oracle.parse(cnf_text("prime-16bit" if name != "prime-16bit" else "rsaFACT-16bit"))
+        bad_clause = [(c.copy(), h.copy()) for c, h in items]
+        bad_clause[len(items) // 2][0][3, 1] *= -1
+        bad_choice = [(c.copy(), h.copy()) for c, h in items]
+        bad_choice[1][1][-1] *= -1
+        for label, its, root in [("other root", items, other), ("clause", bad_clause, A), ("choice", bad_choice, A)]:
+            fr3 = nd.frontier_from_host(its)
+            assert fr3.attach_root(root) is False, (name, label)
+            r3 = fr3.dfs_shard()                       # still searchable, on exactly the loaded sets
+            for k in (0, 1, len(its) // 2):
+                od = oracle.dfs(its[k][0])
+                assert int(r3["verdict"][k]) == (1 if od["models"] else 0), (name, label, k)
+                assert int(r3["nodes"][k]) == od["nodes"], (name, label, k)
+            fr3.free()
+        fr.free()
+        fr2.free()
+
+
 def test_sharding_does_not_change_answers(nd, oracle, cnf_text):
     """Static interleaved shards k -> k mod G (G = 1,2,4,8) reproduce the single-shard verdict
     vector; the global winner is the minimum over shards."""
