@@ -65,7 +65,7 @@ cudaError_t dev_alloc(T** p, size_t bytes) {
 template <class T>
 cudaError_t dev_free(T* p) { return p ? cudaFreeAsync((void*)p, 0) : cudaSuccess; }
 
-// Mapped pinned scratch records (BFS level totals, trunk state): cudaHostAlloc costs about a
+// Mapped pinned scratch records (BFS level totals): cudaHostAlloc costs about a
 // millisecond, so each (host thread, device, slot) gets one allocation that is kept for the
 // life of the process.
 void* pinned_scratch(int slot, size_t bytes) {
@@ -618,23 +618,6 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         st.tree_count = 1;
         f->h2d_bytes += sizeof root + 12;
     }
-    // trunk kernel (index engine): as many warps as state slots fit one CTA's shared memory, <= 32
-    int trunk_warps = 0;
-    bool trunk_ok = true;
-    volatile TrunkState* h_trunk = nullptr;
-    TrunkState* d_trunk = nullptr;
-    struct { void* p = nullptr; } trunk_mem;
-    if (use_index && getenv("NDP_TRUNK")) {   // off by default: the windowed persistent kernel is faster from level 0
-        trunk_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
-        if (trunk_warps >= 2) {
-            trunk_mem.p = pinned_scratch(1, sizeof(TrunkState));
-            if (!trunk_mem.p) return fail(NDP_E_NOMEM, "pinned host scratch");
-            h_trunk = static_cast<volatile TrunkState*>(trunk_mem.p);
-            CUDA_TRY(cudaHostGetDevicePointer((void**)&d_trunk, trunk_mem.p, 0));
-            CUDA_TRY(cudaFuncSetAttribute(bfs_index_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(trunk_warps * slot_bytes)));
-        } else trunk_warps = 0;
-    }
     // persistent level loop (index engine): cooperative launch, one CTA per SM
     bool persist_ok = false, persist_rearm = false;
     size_t persist_cap = 0;
@@ -698,34 +681,6 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         // can any stop test fire inside this level?  -q: the queue never exceeds m + pushes <= 2m;
         // -d: the level is consumed whole iff it + m < D.
         const bool safe = !stop_at_top && (Q > 0 ? 2 * m < (size_t)Q : (it + (long long)m < (long long)D));
-        if (use_index && safe && trunk_warps > 0 && m <= (size_t)trunk_warps && trunk_ok) {
-            // narrow levels: one CTA runs level after level on the device (bfs_index_trunk_kernel)
-            const int max_levels = 4096;
-            if ((status = ensure_arena(f->sbuf[cur_buf ^ 1], f->scap_slots[cur_buf ^ 1], 64, slot_bytes))) break;
-            if ((status = st.reserve_nodes(64)) || (status = st.reserve_tree(st.tree_count + (size_t)max_levels * 64))) break;
-            TrunkState ts;
-            ts.m = (int)m; ts.cur = st.cur; ts.cur_buf = cur_buf; ts.levels_done = 0;
-            ts.it = it; ts.task_count = task_count; ts.evals = 0; ts.tree_count = (unsigned)st.tree_count; ts.pad = 0;
-            memcpy((void*)h_trunk, &ts, sizeof ts);
-            bfs_index_trunk_kernel<<<1, trunk_warps * 32, (size_t)trunk_warps * slot_bytes>>>(
-                *ix, f->sbuf[0], f->sbuf[1], st.nodes[0], st.nodes[1], st.node_tree[0], st.node_tree[1], st.tree_parent,
-                st.tree_lit, D, Q, max_levels, d_trunk);
-            cudaError_t te = cudaStreamSynchronize(0);
-            if (te != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS trunk: ") + cudaGetErrorString(te)); break; }
-            memcpy(&ts, (const void*)h_trunk, sizeof ts);
-            f->bfs_launches += 1;
-            f->d2h_bytes += sizeof ts;
-            f->h2d_bytes += sizeof ts;
-            trunk_ok = false;                 // re-armed after the next regular level
-            if (ts.levels_done > 0) {
-                m = (size_t)ts.m; st.cur = ts.cur; cur_buf = ts.cur_buf;
-                it = ts.it; task_count = ts.task_count; f->bfs_evals += ts.evals; st.tree_count = ts.tree_count;
-                n_safe += (size_t)ts.levels_done;
-                t_safe += now_ms() - t_level;
-                continue;
-            }
-        }
-        trunk_ok = true;
         if (persist_ok && !stop_at_top && (Q > 0 || it + (long long)m < (long long)D)) {
             // hand the level loop to the device until a stop level, an empty queue or a full arena
             if (2 * m > persist_cap) persist_cap = std::max(persist_cap * 2, 4 * m);

@@ -222,7 +222,7 @@ __device__ __forceinline__ void slot_load_cg(unsigned* dst_shared, const unsigne
 // One node: stage the parent's slot in S (shared), apply each attempted branch, write open
 // children to dst slots 2j / 2j+1.  ch[0] = LA, ch[1] = RA.
 __device__ __forceinline__ void index_expand_node(const IndexRoot& ix, const unsigned* src,   // no __restrict__:
-                                                  unsigned* dst, int j, const BfsNode nd, unsigned* S,   // the trunk kernel re-reads what it wrote
+                                                  unsigned* dst, int j, const BfsNode nd, unsigned* S,   // a persistent kernel re-reads what it wrote
 
                                                   unsigned lane, BfsChild ch[2]) {
     unsigned* table = S + 3 * ix.bm_words;
@@ -265,94 +265,6 @@ __global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot i
         index_expand_node(ix, src, dst, j, nodes[j], S, lane, ch);
         if (lane == 0) { children[2 * j] = ch[0]; children[2 * j + 1] = ch[1]; }
     }
-}
-
-// The narrow "trunk" of a granulation: while a level has at most W = blockDim/32 nodes and no
-// stop test can fire in it (-q: 2m < Q; -d: it + m < D), ONE CTA runs level after level without
-// returning to the host: a warp per node, the level's children compacted by warp 0 between two
-// __syncthreads.  (For the multiplier CNFs roughly 60 levels pass per doubling of the width, so
-// a third to a half of all levels live here.)  State in/out through `st`.
-struct TrunkState {
-    int m, cur, cur_buf, levels_done;
-    long long it, task_count;
-    unsigned long long evals;
-    unsigned tree_count, pad;
-};
-
-__global__ void __launch_bounds__(1024) bfs_index_trunk_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
-                                                               BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
-                                                               int32_t* ntree1, int32_t* __restrict__ tree_parent,
-                                                               int32_t* __restrict__ tree_lit, int D, int Q,
-                                                               int max_levels, TrunkState* st_io) {
-    extern __shared__ __align__(16) unsigned smem_words[];
-    __shared__ TrunkState st;
-    __shared__ BfsChild sch[64];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int W = blockDim.x >> 5;
-    unsigned* S = smem_words + (size_t)warp * ix.slot_words;
-    if (threadIdx.x == 0) st = *st_io;
-    __syncthreads();
-    for (int level = 0; level < max_levels; ++level) {
-        const int m = st.m;
-        const bool safe = Q > 0 ? 2 * (long long)m < (long long)Q : st.it + m < (long long)D;
-        if (m == 0 || m > W || !safe) break;
-        unsigned* src = st.cur_buf ? sbuf1 : sbuf0;
-        unsigned* dst = st.cur_buf ? sbuf0 : sbuf1;
-        const BfsNode* nodes = st.cur ? nodes1 : nodes0;
-        const int32_t* ntree = st.cur ? ntree1 : ntree0;
-        BfsNode* nnodes = st.cur ? nodes0 : nodes1;
-        int32_t* nntree = st.cur ? ntree0 : ntree1;
-        if ((int)warp < m) {
-            BfsChild ch[2];
-            index_expand_node(ix, src, dst, (int)warp, nodes[warp], S, lane, ch);
-            if (lane == 0) { sch[2 * warp] = ch[0]; sch[2 * warp + 1] = ch[1]; }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // queue order: children of node 0 first, LA before RA (NDP:904-925)
-            unsigned running = 0, expanded = 0;
-            unsigned long long evals = 0;
-            const unsigned lt = lanemask_lt();
-            for (int base = 0; base < 2 * m; base += 32) {
-                const int idx = base + (int)lane;
-                const bool open = idx < 2 * m && sch[idx].n >= 0;
-                const unsigned bal = __ballot_sync(kFullMask, open);
-                if (open) {
-                    const int j = idx >> 1;
-                    const BfsNode nd = nodes[j];
-                    const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
-                    const unsigned pos = running + __popc(bal & lt);
-                    BfsNode nn;
-                    nn.slot = (uint32_t)idx; nn.n = sch[idx].n; nn.kind = sch[idx].kind; nn.lit = sch[idx].lit;
-                    nnodes[pos] = nn;
-                    nntree[pos] = (int32_t)(st.tree_count + pos);
-                    tree_parent[st.tree_count + pos] = ntree[j];
-                    tree_lit[st.tree_count + pos] = (idx & 1) ? -var : var;
-                }
-                running += __popc(bal);
-            }
-            for (int j = (int)lane; j < m; j += 32) {
-                const BfsNode nd = nodes[j];
-                const int var = nd.kind == K_UNIT ? (nd.lit < 0 ? -nd.lit : nd.lit) : nd.lit;
-                if (nd.n > 0 && var != 0) { evals += (unsigned long long)nd.n; ++expanded; }
-            }
-            for (int off = 16; off > 0; off >>= 1) evals += __shfl_down_sync(kFullMask, evals, off);
-            expanded = __reduce_add_sync(kFullMask, expanded);
-            if (lane == 0) {
-                st.it += expanded;                 // NDP:926
-                st.task_count += running;          // NDP:912,923
-                st.evals += evals;
-                st.tree_count += running;
-                st.cur ^= 1;
-                st.cur_buf ^= 1;
-                st.m = (int)running;
-                st.levels_done += 1;
-            }
-        }
-        __threadfence();   // next level's warps read the nodes / slots / tree written above
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *st_io = st;
 }
 
 // The whole level loop on the device (cooperative launch, one CTA per SM), ONE grid.sync per step.
