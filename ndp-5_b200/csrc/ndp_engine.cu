@@ -356,8 +356,9 @@ int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
     r.ix.table_words = (V + 1 + 15) / 16;
     r.ix.sum_words = (r.ix.bm_words + 31) / 32;
     if (r.ix.sum_words > 32 || getenv("NDP_NO_SUMMARY")) r.ix.sum_words = 0;   // > 32768 clauses: plain scan of B[2]
-    r.ix.sum_off = 3 * r.ix.bm_words + r.ix.table_words;
-    r.ix.slot_words = (3 * r.ix.bm_words + r.ix.table_words + r.ix.sum_words + 3) / 4 * 4;
+    r.ix.table_off = 2 * r.ix.bm_words;
+    r.ix.sum_off = r.ix.table_off + r.ix.table_words;
+    r.ix.slot_words = (r.ix.table_off + r.ix.table_words + r.ix.sum_words + 3) / 4 * 4;
     if (r.ix.slot_words == 0) r.ix.slot_words = 4;
     f->root_indexes.push_back(r);
     *out = &f->root_indexes.back().ix;

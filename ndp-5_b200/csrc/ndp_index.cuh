@@ -12,9 +12,11 @@
 //                (n_pos / n_neg = how many of the clause's literals are +v / -v, so duplicate
 //                literals and tautologies need no special case)
 //
-// and a node's whole state ("state slot") is three bitmaps over root clause ids plus the assignment:
+// and a node's whole state ("state slot") is two bit-planes over root clause ids plus the assignment:
 //
-//   B[k] (k = 0,1,2)  clause is live and currently has exactly k zero literals
+//   P0, P1            2 bits per clause, (P1,P0): 00 gone (satisfied), 01 live with no zero literal,
+//                     10 live with one, 11 live with two.  In the text below B[k] = "live with exactly k
+//                     zeros": B[2] = P1 & P0 (the unit clauses), B[1] = P1 & ~P0, B[0] = ~P1 & P0
 //   table             2 bits per variable (0 unassigned, 1 true, 2 false)
 //   S2                one bit per word of B[2] ("this word is non-zero"): the next unit clause -- what
 //                     99.6 % of the reference's nodes ask for -- is two find-first-sets away
@@ -39,17 +41,21 @@ struct IndexRoot {
     const unsigned* occ_off;          // [max_var + 2]
     const unsigned* occ;              // merged occurrence entries
     int bm_words, table_words;
+    int table_off;                    // = 2 * bm_words: the slot is [P0 | P1 | table | S2]
     int sum_words, sum_off;           // summary of B[2]: bit w of word sum_off + (w >> 5) <=> B[2][w] != 0  (sum_words <= 32, or 0: none)
-    int slot_words;                   // 3 * bm_words + table_words + sum_words, rounded up to a multiple of 4
+    int slot_words;                   // 2 * bm_words + table_words + sum_words, rounded up to a multiple of 4
     int n_zero3;                      // root clauses that are {0,0,0} (never leave, always conflict)
     int first_zero3;                  // lowest such index, or -1
 };
 
-// lowest set bit of a bitmap of `words` words, or -1
-__device__ __forceinline__ int bitmap_first(const unsigned* B, int words, unsigned lane) {
-    for (int w0 = 0; w0 < words; w0 += 32) {
+// lowest clause of class k (k = 1: one zero literal, k = 0: none) in the two planes, or -1
+__device__ __forceinline__ int planes_first(const IndexRoot& ix, const unsigned* S, int k, unsigned lane) {
+    const unsigned* P0 = S;
+    const unsigned* P1 = S + ix.bm_words;
+    for (int w0 = 0; w0 < ix.bm_words; w0 += 32) {
         const int w = w0 + (int)lane;
-        const unsigned word = w < words ? B[w] : 0u;
+        unsigned word = 0u;
+        if (w < ix.bm_words) { const unsigned a = P0[w], b = P1[w]; word = k == 1 ? (b & ~a) : k == 0 ? (~b & a) : (b & a); }
         const unsigned m = __ballot_sync(kFullMask, word != 0u);
         if (m) {
             const int src = __ffs(m) - 1;
@@ -60,7 +66,7 @@ __device__ __forceinline__ int bitmap_first(const unsigned* B, int words, unsign
     return -1;
 }
 
-// Derive the three bitmaps from the assignment table with one pass over the root.
+// Derive the two planes (and the summary) from the assignment table with one pass over the root.
 // Returns the number of live clauses (all-zero root clauses included: they are part of |A|).
 __device__ __noinline__ int index_rebuild(const IndexRoot& ix, unsigned* B, const unsigned* table, unsigned lane) {
     int n_live = 0;
@@ -91,9 +97,8 @@ __device__ __noinline__ int index_rebuild(const IndexRoot& ix, unsigned* B, cons
         const unsigned b3 = __ballot_sync(kFullMask, live && zc == 3u);
         const int w = base >> 5;
         if (lane == 0) {
-            B[w] = b0;
-            B[ix.bm_words + w] = b1;
-            B[2 * ix.bm_words + w] = b2;
+            B[w] = b0 | b2;                     // P0
+            B[ix.bm_words + w] = b1 | b2;       // P1
         }
         if (b2) sum_acc |= 1u << (w & 31);
         if (ix.sum_words && lane == 0 && ((w & 31) == 31 || w == ix.bm_words - 1)) { B[ix.sum_off + (w >> 5)] = sum_acc; }
@@ -116,11 +121,11 @@ __device__ __forceinline__ void index_choice(const IndexRoot& ix, const unsigned
         if (m) {
             const int src = __ffs(m) - 1;
             const int w = src * 32 + __ffs(__shfl_sync(kFullMask, sw, src)) - 1;
-            c = w * 32 + __ffs(B[2 * ix.bm_words + w]) - 1;
+            c = w * 32 + __ffs(B[w] & B[ix.bm_words + w]) - 1;
         } else c = -1;
-    } else c = bitmap_first(B + 2 * ix.bm_words, ix.bm_words, lane);
+    } else c = planes_first(ix, B, 2, lane);
     const bool unit = c >= 0;
-    if (!unit) c = bitmap_first(B + ix.bm_words, ix.bm_words, lane);
+    if (!unit) c = planes_first(ix, B, 1, lane);
     if (c >= 0) {
         // the clause's literals that are still there (non-zero and unassigned); take the LAST one
         const pclause cl = __ldg(&ix.root[c]);
@@ -134,7 +139,7 @@ __device__ __forceinline__ void index_choice(const IndexRoot& ix, const unsigned
         return;
     }
     // neither units nor one-zero clauses: |A[0].l[0]| (NDP:778-779)
-    c = bitmap_first(B, ix.bm_words, lane);
+    c = planes_first(ix, B, 0, lane);
     kind = K_DECIDE;
     if (ix.first_zero3 >= 0 && (c < 0 || ix.first_zero3 < c)) { lit = 0; return; }   // A[0] is {0,0,0}
     const int l = code_lit(__ldg(&ix.root[c]).x & 0xffffu);
@@ -156,25 +161,23 @@ __device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, in
         const unsigned c = e & 0xffffffu, n_pos = (e >> 24) & 3u, n_neg = (e >> 26) & 3u;
         const unsigned w = c >> 5, bit = 1u << (c & 31u);
         int k = -1;
+        unsigned p0 = 0u, p1 = 0u;
         if (i < b) {
-            if (B[w] & bit) k = 0;
-            else if (B[ix.bm_words + w] & bit) k = 1;
-            else if (B[2 * ix.bm_words + w] & bit) k = 2;
+            p0 = B[w] & bit;
+            p1 = B[ix.bm_words + w] & bit;
+            k = (p1 ? 2 : 0) + (p0 ? 1 : 0) - 1;   // -1: already satisfied earlier on this path
         }
-        bool touch2 = false;   // this lane changed word w of B[2]
-        if (k >= 0) {          // else: already satisfied earlier on this path
+        bool touch2 = false;   // this lane changed word w of B[2] = P1 & P0
+        if (k >= 0) {
             const unsigned n_true = t > 0 ? n_pos : n_neg, n_false = t > 0 ? n_neg : n_pos;
-            if (n_true) {
-                ++dropped;
-                if (kWrite) { atomicAnd(&B[k * ix.bm_words + w], ~bit); touch2 = k == 2; }
-            } else {
-                const int k2 = k + (int)n_false;
-                if (k2 >= 3) confl = true;
-                if (kWrite) {
-                    atomicAnd(&B[k * ix.bm_words + w], ~bit);
-                    if (k2 < 3) atomicOr(&B[k2 * ix.bm_words + w], bit);
-                    touch2 = k == 2 || k2 == 2;
-                }
+            const int k2 = n_true ? -1 : k + (int)n_false;      // class afterwards; -1 / >= 3: the clause leaves the planes
+            if (n_true) ++dropped;
+            else if (k2 >= 3) confl = true;
+            if (kWrite && k2 != k) {
+                const unsigned code2 = (k2 >= 0 && k2 < 3) ? (unsigned)(k2 + 1) : 0u;
+                if ((p0 != 0u) != ((code2 & 1u) != 0u)) atomicXor(&B[w], bit);                  // only this lane owns the bit
+                if ((p1 != 0u) != ((code2 & 2u) != 0u)) atomicXor(&B[ix.bm_words + w], bit);
+                touch2 = k == 2 || code2 == 3u;
             }
         }
         if (kWrite && ix.sum_words) {
@@ -185,7 +188,7 @@ __device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, in
             if (touch2) {
                 unsigned* sp = &B[ix.sum_off + (w >> 5)];
                 const unsigned sbit = 1u << (w & 31u);
-                if (B[2 * ix.bm_words + w]) atomicOr(sp, sbit);
+                if (B[w] & B[ix.bm_words + w]) atomicOr(sp, sbit);
                 else atomicAnd(sp, ~sbit);
             }
         }
@@ -225,7 +228,7 @@ __device__ __forceinline__ void index_expand_node(const IndexRoot& ix, const uns
                                                   unsigned* dst, int j, const BfsNode nd, unsigned* S,   // a persistent kernel re-reads what it wrote
 
                                                   unsigned lane, BfsChild ch[2]) {
-    unsigned* table = S + 3 * ix.bm_words;
+    unsigned* table = S + ix.table_off;
     const unsigned* parent = src + (size_t)nd.slot * ix.slot_words;
     ch[0].n = ch[1].n = -1;
     ch[0].kind = ch[1].kind = K_EMPTY;
@@ -329,7 +332,7 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
                                                  BfsChild* children, short* paths, unsigned& my_exp, unsigned& my_push,
                                                  unsigned& my_br, unsigned long long& my_ev) {
     // my_*: lane r accumulates the counters of relative level r (summed over the warp's nodes by the caller)
-    unsigned* table = S + 3 * ix.bm_words;
+    unsigned* table = S + ix.table_off;
     __syncwarp();
     slot_load_cg(S, src + (size_t)nd.slot * ix.slot_words, ix.slot_words, lane);
     __syncwarp();
@@ -697,10 +700,10 @@ __global__ void __launch_bounds__(128) index_states_kernel(const IndexRoot ix, c
     const unsigned lane = threadIdx.x & 31u;
     const int warps_per_block = blockDim.x >> 5;
     unsigned* S = smem_words + (size_t)(threadIdx.x >> 5) * ix.slot_words;
-    unsigned* table = S + 3 * ix.bm_words;
+    unsigned* table = S + ix.table_off;
     for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block) {
         __syncwarp();
-        for (int w = lane; w < ix.slot_words - 3 * ix.bm_words; w += 32)
+        for (int w = lane; w < ix.slot_words - ix.table_off; w += 32)
             table[w] = w < ix.table_words ? __ldg(&tables[(size_t)q * ix.table_words + w]) : 0u;
         __syncwarp();
         const int n_live = index_rebuild(ix, S, table, lane);
@@ -720,7 +723,7 @@ __global__ void __launch_bounds__(128) index_materialise_kernel(const IndexRoot 
     const unsigned lane = threadIdx.x & 31u;
     const int warps_per_block = blockDim.x >> 5;
     for (int q = blockIdx.x * warps_per_block + (threadIdx.x >> 5); q < count; q += gridDim.x * warps_per_block) {
-        const unsigned* table = slot_ptr[q] + 3 * ix.bm_words;
+        const unsigned* table = slot_ptr[q] + ix.table_off;
         SetInfo s = warp_rebuild<true>(ix.root, ix.n_root, out + (size_t)q * stride, table, lane);
         if (lane == 0 && out_n) out_n[q] = s.n;
     }
@@ -798,7 +801,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
     const unsigned gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* mine = smem_raw + (size_t)warp * p.warp_bytes;
     unsigned* B = reinterpret_cast<unsigned*>(mine);
-    unsigned* table = B + 3 * ix.bm_words;
+    unsigned* table = B + ix.table_off;
     unsigned* pend = reinterpret_cast<unsigned*>(mine + p.off_pend);
     short* trail = p.trails + (size_t)gwarp * p.trail_cap;
     unsigned* snap = p.snaps + (size_t)gwarp * p.snap_depth * ix.slot_words;
@@ -916,7 +919,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
                 continue;
             }
             snap_low = min(snap_low, npend);   // siblings pushed from here on have intact snapshots again
-            for (int w = lane; w < ix.table_words; w += 32) table[w] = __ldg(&slot[3 * ix.bm_words + w]);
+            for (int w = lane; w < ix.table_words; w += 32) table[w] = __ldg(&slot[ix.table_off + w]);
             __syncwarp();
             __threadfence_block();
             for (int j = lane; j < ntrail; j += 32) {

@@ -125,7 +125,7 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
         for (int i = lane; i < ix.slot_words / 4; i += 32) d4[i] = __ldcg(&s4[i]);
         ch[0].n = nd.n; ch[0].kind = nd.kind; ch[0].lit = nd.lit;
     } else {
-        unsigned* table = S + 3 * ix.bm_words;
+        unsigned* table = S + ix.table_off;
         __syncwarp();
         slot_load_cg(S, src, ix.slot_words, lane);
         __syncwarp();
