@@ -56,9 +56,9 @@ int ndp_device_count(int* count);
 /* DFS engine: both visit the reference's nodes in the reference's order and return identical
  * results and counters.  SCAN streams each node's clause set (the reference's own data flow,
  * NDP:654-697, from shared memory); INDEX walks a per-variable occurrence index of the root
- * clause array and keeps a node as three bitmaps.  AUTO = INDEX where the frontier came from
- * ndp_bfs (a common root exists), SCAN for ndp_frontier_from_host.  Env NDP_ENGINE=scan|index
- * overrides AUTO. */
+ * clause array and keeps a node as two bit-planes over its clause ids.  AUTO = INDEX where the
+ * frontier has a root (it came from ndp_bfs, or ndp_frontier_attach_root accepted one), SCAN for a
+ * bare ndp_frontier_from_host.  Env NDP_ENGINE=scan|index overrides AUTO. */
 enum { NDP_ENGINE_AUTO = 0, NDP_ENGINE_SCAN = 1, NDP_ENGINE_INDEX = 2 };
 int ndp_set_engine(int engine);
 /* DFS work decomposition (index engine).  The reference's Satisfy_iterative is sequential inside

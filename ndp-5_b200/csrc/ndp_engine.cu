@@ -2,7 +2,7 @@
 // driver with the reference's exact -d/-q stop rules, DFS launch, result gather.
 // Two complete pipelines share the driver (ndp_set_engine / env NDP_ENGINE):
 //   scan  : nodes are clause sets (8-byte records) in fixed-stride slots; kernels in ndp_kernels.cuh
-//   index : nodes are state slots (3 bitmaps + assignment table) over one occurrence index of the
+//   index : nodes are state slots (2 bit-planes + assignment table) over one occurrence index of the
 //           root; kernels in ndp_index.cuh; clause lists are materialised on demand
 // There is no CPU fallback in this file: every compute entry point needs a CUDA device.
 #include "../../include/ndp_b200.h"
