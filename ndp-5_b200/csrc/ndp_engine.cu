@@ -690,7 +690,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
             if (status == NDP_E_NOMEM) { cudaGetLastError(); g_err.clear(); status = NDP_OK; persist_ok = false; }
             if (status) break;
             if (persist_ok) {
-                const size_t tree_room = std::max<size_t>(16 * persist_cap, (size_t)4 << 20);
+                const size_t tree_room = std::max<size_t>(16 * persist_cap, (size_t)5 << 20);   // a window of K levels appends K entries per output
                 if ((status = st.reserve_nodes(persist_cap)) || (status = st.reserve_tree(st.tree_count + tree_room))) break;
                 PersistState ps;
                 memset(&ps, 0, sizeof ps);

@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot i
 // UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
 enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4 };
 constexpr int kPersistMaxBlockNodes = 2048;   // nodes of one level a CTA can own (shared-memory scan arrays)
-constexpr int kWindowMax = 16;                // levels per window
-constexpr int kWindowFan = 4;                 // descendants one node may emit per window (else the window is redone)
-constexpr int kWindowPend = 3;                // pending RA siblings one warp can hold (snapshots in global scratch)
+constexpr int kWindowMax = 32;                // levels per window
+constexpr int kWindowFan = 8;                 // descendants one node may emit per window of > 16 levels (4 up to 16 levels); else the window is redone
+constexpr int kWindowPend = 4;                // pending RA siblings one warp can hold (snapshots in global scratch)
 struct PersistState {
     int m, cur, cur_buf, levels_done, exit_reason, window;
     long long it, task_count;
@@ -328,7 +328,7 @@ struct PersistScratch {           // zeroed by the host before every launch
 // dst[kWindowFan * j + e], metadata children[kWindowFan * j + e], choices paths[(kWindowFan * j + e) * kWindowMax + r].
 // Returns the output count, or -1 if the node needs more than kWindowFan outputs / kWindowPend snapshots.
 __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsigned* src, unsigned* dst, int j,
-                                                 const BfsNode nd, unsigned* S, unsigned* snap, unsigned lane, int K,
+                                                 const BfsNode nd, unsigned* S, unsigned* snap, unsigned lane, int K, int fan,
                                                  BfsChild* children, short* paths, unsigned& my_exp, unsigned& my_push,
                                                  unsigned& my_br, unsigned long long& my_ev) {
     // my_*: lane r accumulates the counters of relative level r (summed over the warp's nodes by the caller)
@@ -343,8 +343,8 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
     for (;;) {
         bool backtrack = false;
         if (r == K) {
-            if (out == kWindowFan) return -1;
-            const size_t o = (size_t)kWindowFan * j + out;
+            if (out == fan) return -1;
+            const size_t o = (size_t)fan * j + out;
             slot_copy(dst + o * ix.slot_words, S, ix.slot_words, lane);
             if ((int)lane < K) paths[o * kWindowMax + lane] = (short)my_path;
             if (lane == 0) { BfsChild c; c.n = n_live; c.kind = kind; c.lit = lit; c.empty = 0; children[o] = c; }
@@ -461,9 +461,13 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
         if (reason != PEXIT_NONE) break;   // uniform: every thread holds the same state
         // window length of this step: K levels need kWindowFan slots / node entries per node and K tree entries per output
         int K = Kcur;
-        if (K > 1 && ((unsigned long long)kWindowFan * m > cap_slots || (unsigned long long)kWindowFan * m > cap_nodes ||
-                      tree_count + (unsigned long long)kWindowFan * m * K > cap_tree)) K = 1;
-        const int fan = K > 1 ? kWindowFan : 2;
+        auto fits = [&](int k) {   // k levels need fan(k) slots / node entries per node and k tree entries per output
+            const unsigned long long fk = k > 16 ? kWindowFan : 4;
+            return fk * m <= cap_slots && fk * m <= cap_nodes && tree_count + fk * m * k <= cap_tree;
+        };
+        if (K > 16 && !fits(K)) K = 16;
+        if (K > 1 && !fits(K)) K = 1;
+        const int fan = K > 16 ? kWindowFan : K > 1 ? 4 : 2;
         const unsigned tag = (unsigned)step + 1u;
         const int par = step & 1;
         unsigned* src = cur_buf ? sbuf1 : sbuf0;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                     if (nd.n > 0 && var != 0) { atomicAdd(&s_exp[0], 1u); atomicAdd(&s_ev[0], (unsigned long long)nd.n); }
                 }
             } else {
-                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, children, paths, my_exp, my_push, my_br, my_ev);
+                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, fan, children, paths, my_exp, my_push, my_br, my_ev);
                 if (lane == 0) {
                     s_cnt[k] = (unsigned char)(c < 0 ? 0 : c);
                     if (c < 0) s_overflow = 1u;
@@ -593,12 +597,12 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                 if (stop) *(volatile unsigned*)&scratch->stop_tag[par] = tag;
             } else {
                 // one thread per (node, output, relative level): K chained tree entries per output
-                const int per_node = kWindowFan * K;
+                const int per_node = fan * K;
                 for (int i = (int)tid; i < nb * per_node; i += (int)blockDim.x) {
                     const int k = i / per_node, rem = i - k * per_node, e = rem / K, r = rem - e * K, j = j0 + k;
                     if (e >= (int)s_cnt[k]) continue;
                     const unsigned pos = base + s_off[k] + (unsigned)e;
-                    const size_t o = (size_t)kWindowFan * j + e;
+                    const size_t o = (size_t)fan * j + e;
                     const unsigned long long t0 = tree_count + (unsigned long long)pos * K;
                     tree_parent[t0 + r] = r == 0 ? __ldcg(&ntree[j]) : (int32_t)(t0 + r - 1);
                     tree_lit[t0 + r] = (int32_t)paths[o * kWindowMax + r];
@@ -629,9 +633,10 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                 s_stop = __ldcg(&scratch->stop_tag[par]) == tag ? 1u : 0u;
             }
         }
-        if (b == 0 && tid >= 32 && tid < 32 + sizeof(PersistAcc) / 4) {
+        if (b == 0 && tid >= 32) {
             // clear the accumulator of step + 2: last read before this step's barrier, next written after the next one
-            reinterpret_cast<unsigned*>(&scratch->acc[(step + 2) % 3])[tid - 32] = 0u;
+            for (unsigned i = tid - 32; i < sizeof(PersistAcc) / 4; i += blockDim.x - 32)
+                reinterpret_cast<unsigned*>(&scratch->acc[(step + 2) % 3])[i] = 0u;
         }
         __syncthreads();
         if (K == 1) {

@@ -32,7 +32,7 @@ for trial in range(trials):
         A = util_cnf.random_cnf(rng, nv, int(rng.integers(1, 220)), p_unit=0.03, p_binary=0.12, p_dup=0.04, p_taut=0.04)
         mode, value = ("d", int(rng.integers(-3, 80))) if rng.random() < 0.5 else ("q", int(rng.integers(-1, 40)))
     D, ovr, Q = util_cnf.settings_for(mode, value)
-    os.environ["NDP_BFS_WINDOW"] = str(int(rng.choice([1, 2, 3, 5, 8, 16])))
+    os.environ["NDP_BFS_WINDOW"] = str(int(rng.choice([1, 2, 3, 5, 8, 16, 24, 32])))
     nd.set_split(int(rng.choice([-1, 0, 2, 7, 50, 400, 5000])))
     o = orc.bfs(A, D, ovr, Q)
     fr = nd.bfs(A, D, ovr, Q)
