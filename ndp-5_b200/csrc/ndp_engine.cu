@@ -183,6 +183,7 @@ struct ndp_frontier {
         unsigned* own_slots = nullptr;      // state slots built or copied for this shard (else BFS slots are used)
         const unsigned** d_slot_ptr = nullptr;   // [n_local]
         BfsNode* d_meta = nullptr;          // [n_local]
+        double mean_alive = 0;              // average live clauses per subproblem of the shard
     };
     std::vector<IndexReplica> index_replicas;
 
@@ -1267,6 +1268,8 @@ int build_index_replica(ndp_frontier* f, int device, size_t first, size_t stride
     const size_t total = f->entries.size();
     r.n_local = first < total ? (total - first + stride - 1) / stride : 0;
     const size_t nl1 = std::max(r.n_local, (size_t)1);
+    for (size_t q = 0; q < r.n_local; ++q) r.mean_alive += (double)f->entries[first + q * stride].n;
+    if (r.n_local) r.mean_alive /= (double)r.n_local;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(dev_alloc((void**)&r.d_slot_ptr, nl1 * sizeof(unsigned*)));
     CUDA_TRY(dev_alloc(&r.d_meta, nl1 * sizeof(BfsNode)));
@@ -1362,12 +1365,16 @@ struct SplitRun {
 };
 
 // How many pieces the shard should be cut into (0 = leave the subproblems whole).
-// Automatic policy: a shard with fewer units than per_warp pieces per resident warp is cut into that many.
-// Two per warp keep the device busy; searches that run for seconds have heavy-tailed piece sizes and a
-// split level costs about a millisecond, so large CNFs (whose subtrees are deep) are cut finer -- the
-// tail is what bounds an early-exit run.  n_root_clauses = 0: the coarse cut used to share a narrow
-// frontier out over several devices (each device then refines its share).
-size_t split_target(size_t n_sub, int n_warps, int n_root_clauses) {
+// Automatic policy.  WHEN: the shard has fewer units than pieces-per-warp x resident warps AND the cut can
+// pay for itself (a split level costs ~0.1-1 ms): either the shard cannot even occupy a quarter of the warps,
+// or its subproblems are still big -- more than half of the root's clauses alive on average, which for these
+// CNFs means thousands of nodes each.  (32-bit -q 16384 shared out over 8 ranks is 2048 subproblems of ~380
+// nodes: searched whole in 0.87 ms, 0.99 ms with a cut; -q 1024, ~7800 nodes each: 3.8 ms cut, 17.9 ms whole.)
+// HOW FINE: two pieces per warp keep the device busy; searches that run for seconds have heavy-tailed piece
+// sizes, so large CNFs (deep subtrees) are cut finer -- the tail is what bounds an early-exit run.
+// n_root_clauses = 0: the coarse cut that shares a narrow frontier out over several devices (each device then
+// refines its share).  mean_alive = average live clauses per unit of the shard.
+size_t split_target(size_t n_sub, int n_warps, int n_root_clauses, double mean_alive) {
     long long mode = g_split;
     if (mode < 0)
         if (const char* e = getenv("NDP_SPLIT")) mode = !strcmp(e, "off") ? 0 : atoll(e);
@@ -1376,7 +1383,10 @@ size_t split_target(size_t n_sub, int n_warps, int n_root_clauses) {
     size_t per_warp = n_root_clauses > 16384 ? 32 : n_root_clauses > 8192 ? 8 : 2;
     if (n_root_clauses > 0)
         if (const char* e = getenv("NDP_SPLIT_PER_WARP")) per_warp = (size_t)std::max(1, atoi(e));
-    return n_sub < per_warp * (size_t)n_warps ? per_warp * (size_t)n_warps : 0;
+    if (n_sub >= per_warp * (size_t)n_warps) return 0;
+    const bool starved = 4 * n_sub < (size_t)n_warps;
+    const bool deep = n_root_clauses <= 0 || mean_alive > 0.5 * (double)n_root_clauses;
+    return starved || deep ? per_warp * (size_t)n_warps : 0;
 }
 
 int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
@@ -1511,7 +1521,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     // index engine: a shard too narrow for the device is first cut into pieces in DFS order
     SplitRun split;
     if (use_index) {
-        const size_t target = split_target(n_sub, n_warps, ix->n_root);
+        const size_t target = split_target(n_sub, n_warps, ix->n_root, irep->mean_alive);
         if (target > n_sub && (rc = run_split(device, *ix, *irep, target, split, stats))) return rc;
     }
     const size_t nl = split.active ? split.n_pieces : n_sub;         // units the DFS kernel pulls
@@ -2008,7 +2018,11 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
         const int n_warps = iplan.grid * iplan.warps_per_cta;
-        const size_t target = split_target(f->entries.size(), n_warps * n_gpus, 0);
+        double alive = 0;
+        for (const Entry& e : f->entries) alive += (double)e.n;
+        alive /= (double)f->entries.size();
+        const bool worth = 4 * f->entries.size() < (size_t)n_warps * n_gpus || alive > 0.5 * (double)ix->n_root;
+        const size_t target = worth ? split_target(f->entries.size(), n_warps * n_gpus, 0, alive) : 0;
         if (target > f->entries.size()) {
             if (stats) memset(stats, 0, sizeof *stats);
             SplitRun split;

@@ -10,12 +10,13 @@ import ndp5_b200 as nd  # noqa: E402
 
 spec = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+stride = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # emulate rank 0 of `stride` ranks
 name, mode, value, (D, ovr, Q) = bench.parse_workload(spec)
 A = bench.clause_array(name)[0]
 fr = nd.bfs(A, D, ovr, Q)
 ts = []
 for _ in range(reps):
-    r = fr.dfs_shard(early_exit=False, counters=False)
+    r = fr.dfs_shard(first=0, stride=stride, early_exit=False, counters=False)
     ts.append(r["stats"]["kernel_ms"])
-print(spec, "n=%d" % len(fr), "kernel_ms", " ".join("%.3f" % t for t in ts), "nodes", r["stats"]["nodes"],
+print(spec, "stride=%d" % stride, "n=%d" % len(fr), "kernel_ms", " ".join("%.3f" % t for t in ts), "nodes", r["stats"]["nodes"],
       "launches", r["stats"]["launches"])
