@@ -1114,8 +1114,7 @@ int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_
     }
     f->states = true;
     f->materialised = true;   // buf[0] slot k already holds element k's clause list
-    f->replicas.clear();      // (none built yet for a fresh frontier; scan replicas would still be valid)
-    return NDP_OK;
+    return NDP_OK;            // (scan replicas built before the call stay valid: the clause lists did not move)
 #undef ATT_TRY
 }
 
