@@ -377,3 +377,17 @@ def test_full_size_48bit_and_64bit(nd, oracle, cnf_text, request):
         assert d1 * d2 == 209727620799133 and {d1, d2} == {15908531, 13183343}
         assert (r["verdict"][:301] == 0).all() and r["verdict"][301] == 1
     fr.free()
+
+
+def test_bfs_96bit_beyond_the_summary_bitmap(nd, oracle):
+    """A 96-bit multiplier CNF (53 856 clauses, 13 680 variables): more than 32 768 clauses, so the one-word-per-32-words
+    summary of the unit-clause plane no longer fits a warp and the engines scan the plane instead; granulation and a
+    short DFS prefix against the oracle."""
+    import gen_cnf
+    text = gen_cnf.dimacs_text((1 << 95) + 12345678901234567, 96)   # any 96-bit product encodes; it need not be a semiprime
+    A = oracle.parse(text)
+    assert A.shape[0] > 32768
+    for mode, value in (("d", 300), ("q", 24)):
+        D, ovr, Q = util_cnf.settings_for(mode, value)
+        fr, o = check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, ("96bit", mode, value))
+        fr.free()
