@@ -142,6 +142,32 @@ int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, 
                   uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
                   uint64_t* nodes, uint64_t* evals, ndp_stats* stats);
 
+/* ---- early exit across processes (one process per GPU) -------------------------------------
+ * The reference ends the job when the first worker reports a model (TAG_SOLUTION_FOUND, NDP:1297-1303,
+ * 1436): rank 0 then tells every worker to stop.  With one process per GPU and no dispatcher, the same
+ * signal is one 8-byte word per device holding the lowest SAT subproblem index known so far: the kernel
+ * that finds a model lowers its own word and every peer's (system-scope atomicMin over NVLink), and
+ * every kernel polls its own.  A word is created on the calling process's current device, exported as
+ * a 64-byte CUDA IPC handle (ship it with any transport: bench.py uses one NCCL all-gather), and
+ * imported by the other processes. */
+typedef struct ndp_exit_word ndp_exit_word;
+enum { NDP_EXIT_HANDLE_BYTES = 64 };
+int ndp_exit_word_create(ndp_exit_word** word);
+int ndp_exit_word_export(const ndp_exit_word* word, uint8_t handle[NDP_EXIT_HANDLE_BYTES]);
+int ndp_exit_word_import(const uint8_t handle[NDP_EXIT_HANDLE_BYTES], ndp_exit_word** peer);
+int ndp_exit_word_reset(ndp_exit_word* word);                       /* back to "no model known" (own words only) */
+int ndp_exit_word_read(const ndp_exit_word* word, size_t* lowest);  /* SIZE_MAX: none */
+void ndp_exit_word_free(ndp_exit_word* word);
+
+/* ndp_dfs_shard with the early-exit words above instead of the in/out hint: `own` is this process's word,
+ * peers[0..n_peers) the imported words of the other ranks (n_peers <= 7).  Subproblems above the lowest
+ * SAT index seen in `own` are abandoned (NDP_NOT_RUN), those below always finish, so the winner of the
+ * job -- the minimum of the ranks' winners -- is the same as on one GPU. */
+int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early_exit, ndp_exit_word* own,
+                         ndp_exit_word* const* peers, int n_peers, uint8_t* verdict, size_t* winner,
+                         int32_t* model, size_t model_cap, size_t* model_len, uint64_t* nodes, uint64_t* evals,
+                         ndp_stats* stats);
+
 /* Whole frontier on n_gpus devices of this process (static interleaved split k -> k mod n_gpus,
  * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1. */
 int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,

@@ -1999,6 +1999,107 @@ int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, 
     return NDP_OK;
 }
 
+struct ndp_exit_word {
+    unsigned long long* ptr = nullptr;   // device memory: own (cudaMalloc) or another process's, mapped through CUDA IPC
+    bool imported = false;
+    int device = 0;
+};
+
+int ndp_exit_word_create(ndp_exit_word** word) {
+    if (!word) return fail(NDP_E_INVALID, "word is null");
+    *word = nullptr;
+    int rc = check_device();
+    if (rc) return rc;
+    std::unique_ptr<ndp_exit_word> w(new ndp_exit_word);
+    w->device = g_device;
+    CUDA_TRY(cudaMalloc(&w->ptr, 8));   // a plain allocation: pool memory cannot be exported over IPC
+    const unsigned long long none = ~0ull;
+    CUDA_TRY(cudaMemcpy(w->ptr, &none, 8, cudaMemcpyHostToDevice));
+    *word = w.release();
+    return NDP_OK;
+}
+int ndp_exit_word_export(const ndp_exit_word* word, uint8_t handle[NDP_EXIT_HANDLE_BYTES]) {
+    if (!word || !handle || word->imported) return fail(NDP_E_INVALID, "export needs a word this process created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NDP_EXIT_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, word->ptr));
+    memcpy(handle, &h, sizeof h);
+    return NDP_OK;
+}
+int ndp_exit_word_import(const uint8_t handle[NDP_EXIT_HANDLE_BYTES], ndp_exit_word** peer) {
+    if (!handle || !peer) return fail(NDP_E_INVALID, "null argument");
+    *peer = nullptr;
+    int rc = check_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    std::unique_ptr<ndp_exit_word> w(new ndp_exit_word);
+    w->imported = true;
+    w->device = g_device;
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    w->ptr = static_cast<unsigned long long*>(p);
+    *peer = w.release();
+    return NDP_OK;
+}
+int ndp_exit_word_reset(ndp_exit_word* word) {
+    if (!word || word->imported) return fail(NDP_E_INVALID, "reset needs a word this process created");
+    CUDA_TRY(cudaSetDevice(word->device));
+    const unsigned long long none = ~0ull;
+    CUDA_TRY(cudaMemcpy(word->ptr, &none, 8, cudaMemcpyHostToDevice));
+    return NDP_OK;
+}
+int ndp_exit_word_read(const ndp_exit_word* word, size_t* lowest) {
+    if (!word || !lowest) return fail(NDP_E_INVALID, "null argument");
+    unsigned long long v = ~0ull;
+    CUDA_TRY(cudaMemcpy(&v, word->ptr, 8, cudaMemcpyDeviceToHost));
+    *lowest = v == ~0ull ? SIZE_MAX : (size_t)v;
+    return NDP_OK;
+}
+void ndp_exit_word_free(ndp_exit_word* word) {
+    if (!word) return;
+    if (word->ptr) {
+        cudaSetDevice(word->device);
+        if (word->imported) cudaIpcCloseMemHandle(word->ptr);
+        else cudaFree(word->ptr);
+    }
+    delete word;
+}
+
+int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early_exit, ndp_exit_word* own,
+                         ndp_exit_word* const* peers, int n_peers, uint8_t* verdict, size_t* winner,
+                         int32_t* model, size_t model_cap, size_t* model_len, uint64_t* nodes, uint64_t* evals,
+                         ndp_stats* stats) {
+    if (!f) return fail(NDP_E_INVALID, "frontier is null");
+    if (stride == 0) return fail(NDP_E_INVALID, "stride must be >= 1");
+    if (!own || own->imported) return fail(NDP_E_INVALID, "own must be a word this process created");
+    if (n_peers < 0 || n_peers > 7 || (n_peers && !peers)) return fail(NDP_E_INVALID, "0..7 peer words");
+    int rc = check_device();
+    if (rc) return rc;
+    if (own->device != f->device) return fail(NDP_E_INVALID, "the exit word lives on another device than the frontier");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (model_len) *model_len = 0;
+    std::vector<unsigned long long*> all(1, own->ptr);
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peers[i]) return fail(NDP_E_INVALID, "peer word is null");
+        all.push_back(peers[i]->ptr);
+    }
+    std::vector<int32_t> m;
+    size_t win = SIZE_MAX;
+    rc = dfs_on_device(f, f->device, first, stride, early_exit, own->ptr, all.data(), (int)all.size(), ~0ull, verdict, &win,
+                       &m, nodes, evals, stats);
+    if (rc) return rc;
+    if (winner) *winner = win;
+    if (win != SIZE_MAX) {
+        if (model_len) *model_len = m.size();
+        if (model && !m.empty()) {
+            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, m.data(), m.size() * sizeof(int32_t));
+        }
+    }
+    return NDP_OK;
+}
+
 int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
                   int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats) {
     if (!f) return fail(NDP_E_INVALID, "frontier is null");

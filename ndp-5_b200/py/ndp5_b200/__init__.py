@@ -65,6 +65,15 @@ def _load():
                                     C.c_size_t, _szp, _u64p, _u64p, C.POINTER(Stats)]),
         "ndp_dfs_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u8p, _szp, _i32p, C.c_size_t, _szp,
                                     C.POINTER(Stats)]),
+        "ndp_exit_word_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+        "ndp_exit_word_export": (C.c_int, [C.c_void_p, _u8p]),
+        "ndp_exit_word_import": (C.c_int, [_u8p, C.POINTER(C.c_void_p)]),
+        "ndp_exit_word_reset": (C.c_int, [C.c_void_p]),
+        "ndp_exit_word_read": (C.c_int, [C.c_void_p, _szp]),
+        "ndp_exit_word_free": (None, [C.c_void_p]),
+        "ndp_dfs_shard_shared": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
+                                           C.POINTER(C.c_void_p), C.c_int, _u8p, _szp, _i32p, C.c_size_t, _szp,
+                                           _u64p, _u64p, C.POINTER(Stats)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -104,6 +113,45 @@ def device_count():
     n = C.c_int(0)
     rc = lib.ndp_device_count(C.byref(n))
     return n.value if rc == NDP_OK else 0
+
+
+EXIT_HANDLE_BYTES = 64
+
+
+class ExitWord:
+    """ndp_exit_word: the device-visible early-exit word of one process (create), or another process's word
+    mapped here through its 64-byte CUDA IPC handle (ExitWord.from_handle)."""
+
+    def __init__(self, handle=None):
+        self.h = C.c_void_p(None)
+        if handle is None:
+            _check(lib.ndp_exit_word_create(C.byref(self.h)))
+        else:
+            buf = np.frombuffer(bytes(handle), dtype=np.uint8).copy()
+            assert buf.size == EXIT_HANDLE_BYTES
+            _check(lib.ndp_exit_word_import(buf.ctypes.data_as(_u8p), C.byref(self.h)))
+
+    @classmethod
+    def from_handle(cls, handle):
+        return cls(handle)
+
+    def export(self):
+        buf = np.zeros(EXIT_HANDLE_BYTES, dtype=np.uint8)
+        _check(lib.ndp_exit_word_export(self.h, buf.ctypes.data_as(_u8p)))
+        return buf.tobytes()
+
+    def reset(self):
+        _check(lib.ndp_exit_word_reset(self.h))
+
+    def read(self):
+        v = C.c_size_t(0)
+        _check(lib.ndp_exit_word_read(self.h, C.byref(v)))
+        return None if v.value == SIZE_MAX else v.value
+
+    def free(self):
+        if self.h:
+            lib.ndp_exit_word_free(self.h)
+            self.h = C.c_void_p(None)
 
 
 class Frontier:
@@ -159,6 +207,25 @@ class Frontier:
         return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
                     model=model[:mlen.value].copy(), nodes=nodes[:n], evals=evals[:n], stats=st.as_dict(),
                     exit_flag=None if flag.value == SIZE_MAX else flag.value)
+
+    def dfs_shard_shared(self, own, peers, first=0, stride=1, early_exit=True, model_cap=1 << 16, counters=True):
+        """ndp_dfs_shard_shared: this rank's shard with device-visible early-exit words (own + the other ranks')."""
+        n = len(self)
+        verdict = np.full(max(n, 1), NOT_RUN, dtype=np.uint8)
+        nodes = np.zeros(max(n, 1), dtype=np.uint64)
+        evals = np.zeros(max(n, 1), dtype=np.uint64)
+        winner = C.c_size_t(SIZE_MAX)
+        model = np.zeros(model_cap, dtype=np.int32)
+        mlen = C.c_size_t(0)
+        st = Stats()
+        arr = (C.c_void_p * max(len(peers), 1))(*[p.h for p in peers])
+        _check(lib.ndp_dfs_shard_shared(self.h, first, stride, int(early_exit), own.h, arr, len(peers),
+                                        verdict.ctypes.data_as(_u8p), C.byref(winner), model.ctypes.data_as(_i32p),
+                                        model_cap, C.byref(mlen),
+                                        nodes.ctypes.data_as(_u64p) if counters else None,
+                                        evals.ctypes.data_as(_u64p) if counters else None, C.byref(st)))
+        return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
+                    model=model[:mlen.value].copy(), nodes=nodes[:n], evals=evals[:n], stats=st.as_dict())
 
     def dfs_batch(self, n_gpus=1, early_exit=False, model_cap=1 << 16):
         n = len(self)

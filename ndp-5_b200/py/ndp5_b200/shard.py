@@ -75,3 +75,15 @@ def all_max(dist, value, world, device="cpu"):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def exchange_exit_words(dist, own_handle, rank, world, device="cuda"):
+    """All-gather the ranks' 64-byte early-exit word handles (CUDA IPC); returns the OTHER ranks' handles in rank order.
+    One tiny collective at set-up: the words themselves are then lowered by the kernels over NVLink, no further traffic."""
+    if dist is None or world == 1:
+        return []
+    import torch
+    t = torch.from_numpy(np.frombuffer(own_handle, dtype=np.uint8).copy()).to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return [o.cpu().numpy().tobytes() for r, o in enumerate(outs) if r != rank]

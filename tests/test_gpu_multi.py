@@ -35,3 +35,20 @@ def test_batch_equals_single_device(engine, oracle, golden, cnf_text):
             fr.free()
     finally:
         nd.set_engine("auto")
+
+
+def test_cross_process_early_exit_words():
+    """One process per GPU (torchrun, 2 ranks): exit words exchanged as CUDA IPC handles over NCCL, lowered by the kernels
+    over NVLink; the job's winner and model are the single-GPU ones and the other rank stands down."""
+    import os
+    import subprocess
+    import sys
+    import ndp5_b200 as nd
+    if nd.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29591", os.path.join(root, "tools", "check_shared_exit.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "MISMATCH" not in r.stdout and r.stdout.count(" OK") >= 8

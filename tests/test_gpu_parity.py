@@ -391,3 +391,35 @@ def test_bfs_96bit_beyond_the_summary_bitmap(nd, oracle):
         D, ovr, Q = util_cnf.settings_for(mode, value)
         fr, o = check_bfs_against_oracle(nd, oracle, A, D, ovr, Q, ("96bit", mode, value))
         fr.free()
+
+
+def test_exit_word_single_process(nd, oracle, golden, cnf_text):
+    """ndp_dfs_shard_shared with this process's own early-exit word and no peers equals ndp_dfs_shard(early_exit):
+    same winner, model and verdicts up to the winner; the word ends up holding the winner and can be reset.
+    (The cross-process exchange needs two GPUs: tests/test_gpu_multi.py / tools/check_shared_exit.py.)"""
+    word = nd.ExitWord()
+    assert word.read() is None and len(word.export()) == nd.EXIT_HANDLE_BYTES
+    n = 0
+    for c in golden["cases"]:
+        if "verdict" not in c or c["bits"] > 20:
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        word.reset()
+        r = fr.dfs_shard_shared(word, [], early_exit=True)
+        w = c["winner"]
+        if w >= 0:
+            assert r["winner"] == w and r["model"].tolist() == c["sat"][str(w)]["model"]
+            assert r["verdict"][: w + 1].tolist() == c["verdict"][: w + 1]
+            assert word.read() == w
+        else:
+            assert r["winner"] is None and word.read() is None and r["verdict"].tolist() == c["verdict"]
+        # a word that already knows a lower index makes the whole shard stand down
+        if w > 0:
+            r2 = fr.dfs_shard_shared(word, [], first=w, stride=len(fr) + 1, early_exit=True)   # word still holds w: not below it
+            assert r2["winner"] == w
+        fr.free()
+        n += 1
+    assert n >= 8
+    word.free()
