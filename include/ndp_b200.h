@@ -42,7 +42,7 @@ typedef struct ndp_stats {
     uint64_t nodes;          /* DFS nodes = Satisfy_iterative loop iterations (NDP:801) */
     uint64_t clause_evals;   /* sum of |A| over nodes that ran the resolution pass (NDP:664) */
     uint64_t rebuilds;       /* sibling re-materialisations (engine detail, not in the reference) */
-    double kernel_ms;        /* device time of the DFS kernel(s), CUDA events */
+    double kernel_ms;        /* device time of the DFS kernel(s), the piece split included, CUDA events */
     uint64_t h2d_bytes;      /* host->device bytes moved inside the call */
     uint64_t d2h_bytes;      /* device->host bytes moved inside the call */
     uint64_t launches;       /* kernels launched by the call */
@@ -169,7 +169,9 @@ int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early
                          ndp_stats* stats);
 
 /* Whole frontier on n_gpus devices of this process (static interleaved split k -> k mod n_gpus,
- * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1. */
+ * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1.  A frontier too
+ * narrow for the devices (-d 12, -d 20: ONE subproblem) is first cut into DFS-order pieces on its home
+ * device and the pieces are what the devices share out; results are folded back per subproblem. */
 int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,
                   int32_t* model, size_t model_cap, size_t* model_len, ndp_stats* stats);
 
