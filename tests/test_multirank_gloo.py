@@ -52,6 +52,10 @@ def _worker(rank, world, port, case, out_dir):
     gw = shard.lowest_winner(dist, winner, world)
     gm = shard.broadcast_model(dist, model if winner == gw else None, gw, world)
     total = shard.all_sum(dist, [int((verdict == 1).sum())], world)
+    # the 64-byte early-exit word handles travel the same way (here: stand-in bytes; real handles need GPUs)
+    mine = bytes([rank + 1]) * 64
+    others = shard.exchange_exit_words(dist, mine, rank, world, device="cpu")
+    assert others == [bytes([r + 1]) * 64 for r in range(world) if r != rank]
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), merged=merged, winner=-1 if gw is None else gw,
              model=np.zeros(0, np.int32) if gm is None else gm, n_sat=total[0])
     dist.barrier()
@@ -93,3 +97,4 @@ def test_shard_indices_partition():
             assert sorted(allidx.tolist()) == list(range(n))
     assert shard.gather_verdicts(None, [0, 1, 2], 3, 0, 1).tolist() == [0, 1, 2]
     assert shard.lowest_winner(None, 5, 1) == 5 and shard.lowest_winner(None, None, 1) is None
+    assert shard.exchange_exit_words(None, b"x" * 64, 0, 1) == []
