@@ -154,6 +154,8 @@ struct ndp_frontier {
     struct RootIndex {                      // per device
         int device = -1;
         pclause* d_root = nullptr;
+        uint2* d_hdr = nullptr;
+        uint4* d_rows = nullptr;
         unsigned *d_occ_off = nullptr, *d_occ = nullptr;
         IndexRoot ix;
     };
@@ -229,6 +231,8 @@ struct ndp_frontier {
             RootIndex& r = root_indexes[i];
             cudaSetDevice(r.device);
             if (r.d_root) dev_free(r.d_root);
+            if (r.d_hdr) dev_free(r.d_hdr);
+            if (r.d_rows) dev_free(r.d_rows);
             if (r.d_occ_off) dev_free(r.d_occ_off);
             if (r.d_occ) dev_free(r.d_occ);
         }
@@ -306,49 +310,84 @@ int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
     const int V = f->max_var;
     if (n_root >= (1u << 24)) return fail(NDP_E_UNSUPPORTED, "more than 2^24 root clauses");
     std::vector<pclause> root(std::max(n_root, (size_t)1));
+    // word-merged rows for clauses that hold the variable once; per-clause entries (occ) for the rest
     std::vector<unsigned> off((size_t)V + 2, 0), occ;
+    std::vector<uint2> hdr((size_t)V + 1, make_uint2(0u, 0u));
+    std::vector<uint4> rows;
     r.ix.n_zero3 = 0;
     r.ix.first_zero3 = -1;
     {
-        // counting sort by variable; within a variable the entries stay in clause order
-        auto merged_entry = [&](size_t c, int j, unsigned& entry) -> bool {
+        struct Occ { unsigned c, n_pos, n_neg; };
+        std::vector<unsigned> cnt((size_t)V + 1, 0);
+        auto occurrence = [&](size_t c, int j, Occ& o) -> bool {   // one per (clause, variable): at the variable's first position
             const int32_t* l = &f->root_c3[3 * c];
             if (!l[j]) return false;
             for (int i = 0; i < j; ++i)
-                if (l[i] && std::abs(l[i]) == std::abs(l[j])) return false;   // one merged entry per (clause, variable)
-            unsigned n_pos = 0, n_neg = 0;
+                if (l[i] && std::abs(l[i]) == std::abs(l[j])) return false;
+            o.c = (unsigned)c; o.n_pos = o.n_neg = 0;
             for (int i = 0; i < 3; ++i) {
-                if (l[i] == std::abs(l[j])) ++n_pos;
-                if (l[i] == -std::abs(l[j])) ++n_neg;
+                if (l[i] == std::abs(l[j])) ++o.n_pos;
+                if (l[i] == -std::abs(l[j])) ++o.n_neg;
             }
-            entry = (unsigned)c | (n_pos << 24) | (n_neg << 26);
             return true;
         };
-        unsigned e = 0;
+        Occ o;
         for (size_t c = 0; c < n_root; ++c) {
             const int32_t* l = &f->root_c3[3 * c];
             root[c] = pack_clause(l[0], l[1], l[2]);
             if (!l[0] && !l[1] && !l[2]) { ++r.ix.n_zero3; if (r.ix.first_zero3 < 0) r.ix.first_zero3 = (int)c; }
             for (int j = 0; j < 3; ++j)
-                if (merged_entry(c, j, e)) ++off[(size_t)std::abs(l[j]) + 1];
+                if (occurrence(c, j, o)) {
+                    const size_t v = (size_t)std::abs(l[j]);
+                    if (o.n_pos + o.n_neg == 1) ++cnt[v];        // upper bound of the row length (before merging)
+                    else ++off[v + 1];
+                }
         }
-        for (int v = 0; v <= V; ++v) off[(size_t)v + 1] += off[v];
+        // counting sort by variable; within a variable the entries stay in clause order, so the
+        // clauses of one plane word are adjacent and merge into one row entry
+        std::vector<size_t> start((size_t)V + 2, 0);
+        for (int v = 0; v <= V; ++v) { start[(size_t)v + 1] = start[v] + cnt[v]; off[(size_t)v + 1] += off[v]; }
+        std::vector<uint4> raw(start[(size_t)V + 1]);
+        std::vector<size_t> fill(start.begin(), start.end() - 1);
         occ.resize(off[(size_t)V + 1]);
         std::vector<unsigned> cursor(off.begin(), off.end() - 1);
         for (size_t c = 0; c < n_root; ++c) {
             const int32_t* l = &f->root_c3[3 * c];
             for (int j = 0; j < 3; ++j)
-                if (merged_entry(c, j, e)) occ[cursor[(size_t)std::abs(l[j])]++] = e;
+                if (occurrence(c, j, o)) {
+                    const size_t v = (size_t)std::abs(l[j]);
+                    const unsigned bit = 1u << (c & 31);
+                    if (o.n_pos + o.n_neg == 1) raw[fill[v]++] = make_uint4((unsigned)(c >> 5), o.n_pos ? bit : 0u, o.n_neg ? bit : 0u, 0u);
+                    else occ[cursor[v]++] = o.c | (o.n_pos << 24) | (o.n_neg << 26);
+                }
         }
+        rows.reserve(raw.size());
+        for (int v = 0; v <= V; ++v) {
+            const size_t first = rows.size();
+            for (size_t i = start[v]; i < start[(size_t)v + 1]; ++i) {
+                if (rows.size() > first && rows.back().x == raw[i].x) { rows.back().y |= raw[i].y; rows.back().z |= raw[i].z; }
+                else rows.push_back(raw[i]);
+            }
+            const bool multi = off[(size_t)v + 1] > off[v];
+            hdr[v] = make_uint2((unsigned)first, (unsigned)(rows.size() - first) | (multi ? 0x80000000u : 0u));
+        }
+        if (rows.empty()) rows.push_back(make_uint4(0u, 0u, 0u, 0u));
     }
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(dev_alloc(&r.d_root, root.size() * sizeof(pclause)));
+    CUDA_TRY(dev_alloc(&r.d_hdr, hdr.size() * sizeof(uint2)));
+    CUDA_TRY(dev_alloc(&r.d_rows, rows.size() * sizeof(uint4)));
     CUDA_TRY(dev_alloc(&r.d_occ_off, off.size() * 4));
     CUDA_TRY(dev_alloc(&r.d_occ, std::max(occ.size(), (size_t)1) * 4));
     CUDA_TRY(cudaMemcpy(r.d_root, root.data(), root.size() * sizeof(pclause), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_hdr, hdr.data(), hdr.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_rows, rows.data(), rows.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r.d_occ_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
     if (!occ.empty()) CUDA_TRY(cudaMemcpy(r.d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
-    f->h2d_bytes += root.size() * sizeof(pclause) + off.size() * 4 + occ.size() * 4;
+    f->h2d_bytes += root.size() * sizeof(pclause) + hdr.size() * sizeof(uint2) + rows.size() * sizeof(uint4) + off.size() * 4 +
+                    occ.size() * 4;
+    r.ix.row_hdr = r.d_hdr;
+    r.ix.rows = r.d_rows;
     r.ix.root = r.d_root;
     r.ix.n_root = (int)n_root;
     r.ix.occ_off = r.d_occ_off;
@@ -361,6 +400,7 @@ int get_root_index(ndp_frontier* f, int device, const IndexRoot** out) {
     r.ix.sum_off = r.ix.table_off + r.ix.table_words;
     r.ix.slot_words = (r.ix.table_off + r.ix.table_words + r.ix.sum_words + 3) / 4 * 4;
     if (r.ix.slot_words == 0) r.ix.slot_words = 4;
+    r.ix.plain = r.ix.sum_words > 0 && r.ix.n_zero3 == 0 && occ.empty() && !getenv("NDP_NO_PLAIN");
     f->root_indexes.push_back(r);
     *out = &f->root_indexes.back().ix;
     return NDP_OK;
@@ -627,6 +667,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     size_t ppaths_cap = 0;
     int window_max = kWindowMax;
     if (const char* e = getenv("NDP_BFS_WINDOW")) window_max = std::max(1, std::min(kWindowMax, atoi(e)));
+    int max_block_nodes = kPersistMaxBlockNodes;   // test knob: exercise the wide-level path on small inputs
+    if (const char* e = getenv("NDP_PERSIST_BLOCK_NODES")) max_block_nodes = std::max(1, std::min(kPersistMaxBlockNodes, atoi(e)));
     int coop_grid = 0, coop_warps = 0;
     if (use_index && !getenv("NDP_NO_PERSIST")) {
         int coop = 0, sms = 0;
@@ -718,7 +760,7 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 unsigned* snaps = d_psnaps.as<unsigned>();
                 short* ppaths = d_ppaths.as<short>();
                 void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps, &dsc,
-                                &snaps, &ppaths, &window_max};
+                                &snaps, &ppaths, &window_max, &max_block_nodes};
                 cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid),
                                                              dim3(coop_warps * 32), args, coop_warps * slot_bytes, 0);
                 if (le == cudaSuccess) le = cudaStreamSynchronize(0);
@@ -745,7 +787,10 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                     continue;
                 }
                 if (ps.exit_reason == PEXIT_EMPTY || ps.exit_reason == PEXIT_LEVELS) continue;
-                persist_ok = false;            // PEXIT_HOST_LEVEL: this level goes through the exact per-level path
+                // PEXIT_HOST_LEVEL (a stop test can fire) / PEXIT_WIDE (more nodes per CTA than the kernel's
+                // shared scan arrays hold): this level goes through the per-level path, then the device
+                // loop is re-armed
+                persist_ok = false;
                 persist_rearm = true;
                 continue;
             }
@@ -1031,6 +1076,8 @@ int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_
     auto undo = [&](int code, const std::string& msg) {
         for (auto& r : f->root_indexes) {
             if (r.d_root) dev_free(r.d_root);
+            if (r.d_hdr) dev_free(r.d_hdr);
+            if (r.d_rows) dev_free(r.d_rows);
             if (r.d_occ_off) dev_free(r.d_occ_off);
             if (r.d_occ) dev_free(r.d_occ);
         }
@@ -1592,14 +1639,17 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.snaps = b_snaps.as<unsigned>();
         p.snap_depth = snap_depth;
         p.models = b_models.as<int32_t>();
-        CUDA_TRY(cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
+        // the common case (B[2] summary, no {0,0,0} clause, no variable twice in a clause) runs the kernel
+        // with those tests compiled out
+        auto kern = ix->plain ? dfs_index_kernel<true> : dfs_index_kernel<false>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
         {
             // leave L1 everything the resident CTAs do not need: the root index is read through it
             const size_t need = (size_t)iplan.ctas_per_sm * (iplan.smem_bytes + 1024);
             int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
-            cudaFuncSetAttribute(dfs_index_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
-        dfs_index_kernel<<<iplan.grid, iplan.warps_per_cta * 32, iplan.smem_bytes>>>(p);
+        kern<<<iplan.grid, iplan.warps_per_cta * 32, iplan.smem_bytes>>>(p);
     } else {
         DfsParams& p = plan.p;
         p.sub_base = rep->d_base;

@@ -38,14 +38,24 @@ namespace ndp {
 struct IndexRoot {
     const pclause* root;              // [n_root]
     int n_root;
+    // Occurrence rows, one per variable, MERGED PER BITMAP WORD: entry = {w, pos, neg, 0} says "of the 32
+    // clauses of plane word w, those in `pos` hold +v once, those in `neg` hold -v once".  A resolution
+    // step is then plain word arithmetic on (P0[w], P1[w]) by ONE lane per word -- no per-clause atomics,
+    // no two lanes on one word.  row_hdr[v] = {first entry, entry count | multi << 31}.
+    const uint2* row_hdr;             // [max_var + 1]
+    const uint4* rows;
+    // Clauses that mention a variable more than once ((x, x, y), (x, -x, y): duplicates and tautologies)
+    // are left out of that variable's row and listed here per clause: c | n_pos << 24 | n_neg << 26
+    // (n_pos / n_neg = how many of the clause's literals are +v / -v).  Empty for every generated CNF.
     const unsigned* occ_off;          // [max_var + 2]
-    const unsigned* occ;              // merged occurrence entries
+    const unsigned* occ;
     int bm_words, table_words;
     int table_off;                    // = 2 * bm_words: the slot is [P0 | P1 | table | S2]
     int sum_words, sum_off;           // summary of B[2]: bit w of word sum_off + (w >> 5) <=> B[2][w] != 0  (sum_words <= 32, or 0: none)
     int slot_words;                   // 2 * bm_words + table_words + sum_words, rounded up to a multiple of 4
     int n_zero3;                      // root clauses that are {0,0,0} (never leave, always conflict)
     int first_zero3;                  // lowest such index, or -1
+    int plain;                        // sum_words > 0, n_zero3 == 0 and occ is empty: kernels may use their kPlain instantiation
 };
 
 // lowest clause of class k (k = 1: one zero literal, k = 0: none) in the two planes, or -1
@@ -109,12 +119,41 @@ __device__ __noinline__ int index_rebuild(const IndexRoot& ix, unsigned* B, cons
     return n_live;
 }
 
+// The literal choice() takes from live clause c: the LAST of its literals that is still there
+// (non-zero and unassigned).  Lanes 0..2 test one literal each.
+__device__ __forceinline__ int clause_last_literal(const IndexRoot& ix, const unsigned* table, int c, unsigned lane) {
+    const pclause cl = __ldg(&ix.root[c]);
+    unsigned f = ((lane >= 2u ? cl.y : cl.x) >> ((lane & 1u) << 4)) & 0xffffu;   // code of literal `lane`
+    if (lane > 2u) f = 0u;
+    // f = var << 1 | sign: table word var >> 4 = f >> 5, bit pair (var & 15) * 2 = f & 30
+    const bool there = f != 0u && ((table[f >> 5] >> (f & 30u)) & 3u) == 0u;
+    const unsigned m = __ballot_sync(kFullMask, there);
+    return code_lit(__shfl_sync(kFullMask, f, 31 - __clz((int)m)));
+}
+
+// choice() when no clause has two zeros (NDP:767-779): a decision.  Rare (0.4 % of the DFS nodes).
+__device__ __noinline__ int index_choice_decide(const IndexRoot& ix, const unsigned* B, const unsigned* table, unsigned lane) {
+    int c = planes_first(ix, B, 1, lane);
+    if (c >= 0) {
+        const int l = clause_last_literal(ix, table, c, lane);
+        return l < 0 ? -l : l;
+    }
+    // neither units nor one-zero clauses: |A[0].l[0]| (NDP:778-779)
+    c = planes_first(ix, B, 0, lane);
+    if (ix.first_zero3 >= 0 && (c < 0 || ix.first_zero3 < c)) return 0;   // A[0] is {0,0,0}
+    const int l = code_lit(__ldg(&ix.root[c]).x & 0xffffu);
+    return l < 0 ? -l : l;
+}
+
 // What choice() returns for the current state: kind/lit as in SetInfo.
+// kPlain (here and below): the root has a B[2] summary, no {0,0,0} clause and no clause that mentions a
+// variable twice -- true for every generated factoring CNF -- so the tests for those cases are compiled out.
+template <bool kPlain = false>
 __device__ __forceinline__ void index_choice(const IndexRoot& ix, const unsigned* B, const unsigned* table, int n_live,
                                              unsigned lane, int& kind, int& lit) {
-    if (n_live == 0) { kind = K_EMPTY; lit = 0; return; }
+    if (!kPlain && n_live == 0) { kind = K_EMPTY; lit = 0; return; }
     int c;
-    if (ix.sum_words) {
+    if (kPlain || ix.sum_words) {
         // first unit clause through the summary: one ballot over <= 32 summary words, then one word of B[2]
         const unsigned sw = (int)lane < ix.sum_words ? B[ix.sum_off + lane] : 0u;
         const unsigned m = __ballot_sync(kFullMask, sw != 0u);
@@ -124,37 +163,17 @@ __device__ __forceinline__ void index_choice(const IndexRoot& ix, const unsigned
             c = w * 32 + __ffs(B[w] & B[ix.bm_words + w]) - 1;
         } else c = -1;
     } else c = planes_first(ix, B, 2, lane);
-    const bool unit = c >= 0;
-    if (!unit) c = planes_first(ix, B, 1, lane);
-    if (c >= 0) {
-        // the clause's literals that are still there (non-zero and unassigned); take the LAST one
-        const pclause cl = __ldg(&ix.root[c]);
-        const unsigned f = lane == 0 ? (cl.x & 0xffffu) : lane == 1 ? (cl.x >> 16) : (cl.y & 0xffffu);
-        const bool there = lane < 3 && f != 0u && table_get(table, f >> 1) == 0u;
-        const unsigned m = __ballot_sync(kFullMask, there);
-        const int src = 31 - __clz((int)m);
-        const int l = code_lit(__shfl_sync(kFullMask, f, src));
-        if (unit) { kind = K_UNIT; lit = l; }
-        else { kind = K_DECIDE; lit = l < 0 ? -l : l; }
-        return;
-    }
-    // neither units nor one-zero clauses: |A[0].l[0]| (NDP:778-779)
-    c = planes_first(ix, B, 0, lane);
-    kind = K_DECIDE;
-    if (ix.first_zero3 >= 0 && (c < 0 || ix.first_zero3 < c)) { lit = 0; return; }   // A[0] is {0,0,0}
-    const int l = code_lit(__ldg(&ix.root[c]).x & 0xffffu);
-    lit = l < 0 ? -l : l;
+    if (c >= 0) { kind = K_UNIT; lit = clause_last_literal(ix, table, c, lane); }
+    else { kind = K_DECIDE; lit = index_choice_decide(ix, B, table, lane); }
 }
 
-// Resolution for "literal t becomes true".  kWrite applies it; otherwise it only classifies.
-// Returns the live count afterwards; conflict is raised when a clause reaches three zeros.
+// The per-clause pass over the clauses that mention |t| more than once (IndexRoot::occ).  Per-lane partial
+// results: `dropped` clauses satisfied, `confl` a clause reached three zeros.  kWrite applies the step.
 template <bool kWrite>
-__device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, int n_live, int t, bool& conflict,
-                                            unsigned lane) {
+__device__ __noinline__ void index_assign_multi(const IndexRoot& ix, unsigned* B, int t, unsigned lane, unsigned& dropped,
+                                                bool& confl) {
     const unsigned v = (unsigned)(t < 0 ? -t : t);
     const unsigned a = __ldg(&ix.occ_off[v]), b = __ldg(&ix.occ_off[v + 1]);
-    int dropped = 0;
-    bool confl = false;
     for (unsigned base = a; base < b; base += 32) {   // warp-uniform trip count (the summary fix-up has a warp barrier)
         const unsigned i = base + lane;
         const unsigned e = i < b ? __ldg(&ix.occ[i]) : 0u;
@@ -193,9 +212,109 @@ __device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, in
             }
         }
     }
-    conflict = ix.n_zero3 > 0 || __any_sync(kFullMask, confl);
     if (kWrite) __syncwarp();
-    return n_live - (int)__reduce_add_sync(kFullMask, (unsigned)dropped);
+}
+
+constexpr unsigned kConflBit = 1u << 26;   // per-lane conflict flag riding on the dropped count (n_root < 2^24) through one redux
+
+// One row entry of a resolution step: e = {w, pos, neg, -}.  Returns the entry's contribution to the
+// step's result: clauses satisfied (+ kConflBit if one of the word's clauses reached three zeros).
+template <bool kWrite, bool kPlain>
+__device__ __forceinline__ unsigned index_assign_entry(const IndexRoot& ix, unsigned* B, const uint4 e, bool positive) {
+    const unsigned T = positive ? e.y : e.z, F = positive ? e.z : e.y;
+    unsigned* w0 = B + e.x;
+    unsigned* w1 = w0 + ix.bm_words;
+    unsigned p0 = *w0, p1 = *w1;
+    const unsigned live = p0 | p1, old2 = p0 & p1;
+    const unsigned f = F & live;
+    unsigned acc = (unsigned)__popc(T & live);
+    if (f & old2) acc |= kConflBit;
+    if (kWrite) {
+        p0 &= ~T;
+        p1 &= ~T;
+        const unsigned carry = p0 & f;   // (P1,P0) += 1 on the F bits: 01 -> 10 -> 11 -> (00 + conflict)
+        p0 ^= f;
+        p1 ^= carry;
+        *w0 = p0;
+        *w1 = p1;
+        if ((kPlain || ix.sum_words) && ((old2 != 0u) != ((p0 & p1) != 0u))) {
+            // the word gained its first / lost its last unit clause: one summary bit, owned by this lane
+            unsigned* sp = &B[ix.sum_off + (e.x >> 5)];
+            const unsigned sbit = 1u << (e.x & 31u);
+            if (old2 == 0u) atomicOr(sp, sbit);
+            else atomicAnd(sp, ~sbit);
+        }
+    }
+    return acc;
+}
+
+// Resolution for "literal t becomes true" (NDP:654-697 / 700-750 on the planes).  kWrite applies it;
+// otherwise it only classifies.  Returns the live count afterwards; conflict is raised when a clause
+// reaches three zeros.  One lane per touched plane word: satisfied clauses (T) leave both planes, clauses
+// holding the false literal (F) move up one class -- a 2-bit increment (P1,P0) += 1 on the F bits, whose
+// overflow out of 11 is the conflict.
+template <bool kWrite, bool kPlain = false>
+__device__ __forceinline__ int index_assign(const IndexRoot& ix, unsigned* B, int n_live, int t, bool& conflict,
+                                            unsigned lane) {
+    const unsigned v = (unsigned)(t < 0 ? -t : t);
+    const uint2 hdr = __ldg(&ix.row_hdr[v]);
+    const unsigned cnt = hdr.y & 0x7fffffffu;
+    unsigned acc = 0;   // satisfied clauses + kConflBit per conflict
+    if (lane < cnt) acc = index_assign_entry<kWrite, kPlain>(ix, B, __ldg(&ix.rows[hdr.x + lane]), t > 0);
+    if (cnt > 32u) {    // rows longer than a warp: the multiplier's input bits (decisions only)
+#pragma unroll 1
+        for (unsigned i = lane + 32u; i < cnt; i += 32u) {
+            const unsigned a2 = index_assign_entry<kWrite, kPlain>(ix, B, __ldg(&ix.rows[hdr.x + i]), t > 0);
+            acc = (acc + (a2 & (kConflBit - 1u))) | (a2 & kConflBit);
+        }
+    }
+    if (kWrite) __syncwarp();
+    if (!kPlain && (hdr.y >> 31)) {   // the variable also sits in duplicate-literal / tautological clauses: per-clause pass
+        unsigned dropped = 0;
+        bool confl = false;
+        index_assign_multi<kWrite>(ix, B, t, lane, dropped, confl);
+        acc += dropped;
+        if (confl) acc |= kConflBit;
+    }
+    const unsigned total = __reduce_add_sync(kFullMask, acc);   // <= 32 flags of 2^26 stay below 2^32
+    conflict = (!kPlain && ix.n_zero3 > 0) || (total >> 26) != 0u;
+    return n_live - (int)(total & (kConflBit - 1u));
+}
+
+// Both children of a decision on variable `var` in one read-only pass: LA = var true, RA = var false.
+__device__ __forceinline__ void index_classify(const IndexRoot& ix, unsigned* B, int n_live, int var, int& la_n, bool& la_conf,
+                                               int& ra_n, bool& ra_conf, unsigned lane) {
+    const uint2 hdr = __ldg(&ix.row_hdr[var]);
+    const unsigned cnt = hdr.y & 0x7fffffffu;
+    unsigned la = 0, ra = 0;
+    for (unsigned base = 0; base < cnt; base += 32) {
+        const unsigned i = base + lane;
+        if (i < cnt) {
+            const uint4 e = __ldg(&ix.rows[hdr.x + i]);
+            const unsigned p0 = B[e.x], p1 = B[ix.bm_words + e.x];
+            const unsigned live = p0 | p1, two = p0 & p1;
+            la += (unsigned)__popc(e.y & live);
+            ra += (unsigned)__popc(e.z & live);
+            if (e.z & two) la |= kConflBit;
+            if (e.y & two) ra |= kConflBit;
+        }
+    }
+    if (hdr.y >> 31) {
+        unsigned d = 0;
+        bool c = false;
+        index_assign_multi<false>(ix, B, var, lane, d, c);
+        la += d;
+        if (c) la |= kConflBit;
+        d = 0; c = false;
+        index_assign_multi<false>(ix, B, -var, lane, d, c);
+        ra += d;
+        if (c) ra |= kConflBit;
+    }
+    const unsigned tl = __reduce_add_sync(kFullMask, la), tr = __reduce_add_sync(kFullMask, ra);
+    la_conf = ix.n_zero3 > 0 || (tl >> 26) != 0u;
+    ra_conf = ix.n_zero3 > 0 || (tr >> 26) != 0u;
+    la_n = n_live - (int)(tl & (kConflBit - 1u));
+    ra_n = n_live - (int)(tr & (kConflBit - 1u));
 }
 
 __device__ __forceinline__ void table_set(unsigned* table, int t) {
@@ -290,7 +409,8 @@ __global__ void __launch_bounds__(256) bfs_index_expand_kernel(const IndexRoot i
 //             is redone, shorter, from the untouched source level.
 // The kernel returns to the host only when it has to: the level in which a stop test fires (left
 // UNTOUCHED for the host's exact walk), an empty queue, or arenas that must grow.
-enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4 };
+enum : int { PEXIT_NONE = 0, PEXIT_EMPTY = 1, PEXIT_HOST_LEVEL = 2, PEXIT_CAPACITY = 3, PEXIT_LEVELS = 4,
+              PEXIT_WIDE = 5 };   // WIDE: the level has more nodes per CTA than the shared scan arrays hold
 constexpr int kPersistMaxBlockNodes = 2048;   // nodes of one level a CTA can own (shared-memory scan arrays)
 constexpr int kWindowMax = 32;                // levels per window
 constexpr int kWindowFan = 8;                 // descendants one node may emit per window of > 16 levels (4 up to 16 levels); else the window is redone
@@ -361,8 +481,8 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
                     t = lit;              // the other branch falsifies the unit clause: {0,0,0}, never pushed
                 } else {
                     bool la_conf, ra_conf;
-                    const int la_n = index_assign<false>(ix, S, n_live, var, la_conf, lane);
-                    const int ra_n = index_assign<false>(ix, S, n_live, -var, ra_conf, lane);
+                    int la_n, ra_n;
+                    index_classify(ix, S, n_live, var, la_n, la_conf, ra_n, ra_conf, lane);
                     const bool la_open = la_n > 0 && !la_conf, ra_open = ra_n > 0 && !ra_conf;   // NDP:908,919
                     if (la_open && ra_open) {
                         if (npend == kWindowPend) return -1;
@@ -420,7 +540,7 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                                                                    int32_t* tree_parent, int32_t* tree_lit, int D, int Q,
                                                                    int ovr, int max_levels, PersistState* st,
                                                                    PersistScratch* scratch, unsigned* snaps, short* paths,
-                                                                   int window_max) {
+                                                                   int window_max, int max_block_nodes) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned smem_words[];
@@ -455,8 +575,8 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
         if (m == 0) reason = PEXIT_EMPTY;
         else if ((Q > 0 && m >= Q) || (D == -1 && !ovr)) reason = PEXIT_HOST_LEVEL;          // NDP:894-897 at the level's first pop
         else if (Q <= 0 && it + m >= (long long)D) reason = PEXIT_HOST_LEVEL;                // the -d budget ends inside this level
-        else if (2ull * m > cap_slots || 2ull * m > cap_nodes || tree_count + 2ull * m > cap_tree ||
-                 (m + G - 1) / G > kPersistMaxBlockNodes) reason = PEXIT_CAPACITY;
+        else if ((m + G - 1) / G > max_block_nodes) reason = PEXIT_WIDE;   // this level goes through the per-level kernels
+        else if (2ull * m > cap_slots || 2ull * m > cap_nodes || tree_count + 2ull * m > cap_tree) reason = PEXIT_CAPACITY;
         else if (levels_done >= max_levels) reason = PEXIT_LEVELS;
         if (reason != PEXIT_NONE) break;   // uniform: every thread holds the same state
         // window length of this step: K levels need kWindowFan slots / node entries per node and K tree entries per output
@@ -798,6 +918,7 @@ struct IndexParams {
     int warp_bytes, off_pend;         // shared memory of one warp: state slot, then pend
 };
 
+template <bool kPlain>
 __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant__ IndexParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const IndexRoot& ix = p.ix;
@@ -808,7 +929,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
     unsigned* B = reinterpret_cast<unsigned*>(mine);
     unsigned* table = B + ix.table_off;
     unsigned* pend = reinterpret_cast<unsigned*>(mine + p.off_pend);
-    short* trail = p.trails + (size_t)gwarp * p.trail_cap;
+    const unsigned tbase = gwarp * (unsigned)p.trail_cap;   // this warp's trail: p.trails[tbase + i] (32-bit index arithmetic)
     unsigned* snap = p.snaps + (size_t)gwarp * p.snap_depth * ix.slot_words;
 
     for (;;) {
@@ -838,36 +959,30 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
         }
         __syncwarp();
         if (kind == K_LEAF) verdict = 1;   // the split already reached the model: no node left to visit
-        else for (;;) {
+        else if (n_live == 0 || lit == 0) { nodes = 1; verdict = 1; }   // choice()==0 at the piece's own root (NDP:817-823);
+        else for (;;) {                                                 // below it every node has a literal to branch on
             ++nodes;  // one Satisfy_iterative loop iteration (NDP:801-806)
             if ((nodes & 63u) == 0 &&
                 ((p.early_exit && *(volatile unsigned long long*)p.best < g) || *my_best < q)) { verdict = 2; break; }
-            const int var = kind == K_UNIT ? (lit < 0 ? -lit : lit) : lit;
-            if (n_live == 0 || var == 0) { verdict = 1; break; }   // choice()==0: record choices (NDP:817-823)
+            const int var = lit < 0 ? -lit : lit;                  // K_DECIDE carries the variable itself
             evals += (unsigned long long)n_live;                   // one ResolutionStepWithConflict (NDP:831)
-            int t = 0;
-            bool pending = false;
-            if (kind == K_UNIT) {
-                t = lit;   // the other branch falsifies the unit clause: {0,0,0}, never pushed
-            } else {
+            int t = lit;   // unit clause: the other branch falsifies it ({0,0,0}, never pushed)
+            if (kind != K_UNIT) {
                 bool la_conf, ra_conf;
-                const int la_n = index_assign<false>(ix, B, n_live, var, la_conf, lane);
+                int la_n, ra_n;
+                index_classify(ix, B, n_live, var, la_n, la_conf, ra_n, ra_conf, lane);
                 if (la_n == 0) {                                    // LA empty wins first (NDP:843-850)
-                    if (lane == 0) trail[ntrail] = (short)var;
+                    if (lane == 0) p.trails[tbase + (unsigned)(ntrail)] = (short)var;
                     ++ntrail; verdict = 1; break;
                 }
-                const int ra_n = index_assign<false>(ix, B, n_live, -var, ra_conf, lane);
                 if (ra_n == 0) {                                    // NDP:863-870
-                    if (lane == 0) trail[ntrail] = (short)(-var);
+                    if (lane == 0) p.trails[tbase + (unsigned)(ntrail)] = (short)(-var);
                     ++ntrail; verdict = 1; break;
                 }
-                if (!ra_conf) { t = -var; pending = !la_conf; }     // RA is explored first
-                else if (!la_conf) t = var;
-            }
-            bool dead = t == 0;
-            if (!dead) {
-                if (pending) {
-                    // keep the state before the branch: the LA sibling is one resolution step away from it
+                t = !ra_conf ? -var : (!la_conf ? var : 0);         // RA is explored first
+                if (!ra_conf && !la_conf) {
+                    // both open: LA stays pending.  Keep the state before the branch: the LA sibling is one
+                    // resolution step away from it
                     if (p.snap_depth > 0) {
                         const int k = npend % p.snap_depth;
                         __syncwarp();
@@ -876,18 +991,22 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
                         snap_low = max(min(snap_low, npend), npend - p.snap_depth + 1);
                     }
                     ++npend;
+                    if (lane == 0) pend[ntrail >> 5] |= 1u << (ntrail & 31);
                 }
-                if (lane == 0) {
-                    if (pending) pend[ntrail >> 5] |= 1u << (ntrail & 31);
-                    trail[ntrail] = (short)t;
-                    table_set(table, t);
-                }
+            }
+            if (t != 0) {
+                // every lane stores the same value to the same place: no divergent lane-0 block on the hot path
+                p.trails[tbase + (unsigned)(ntrail)] = (short)t;
+                table_set(table, t);
                 ++ntrail;
                 bool conflict;
-                n_live = index_assign<true>(ix, B, n_live, t, conflict, lane);
+                n_live = index_assign<true, kPlain>(ix, B, n_live, t, conflict, lane);
                 if (n_live == 0) { verdict = 1; break; }            // empty branch => model (NDP:843-852 / 863-872)
-                if (conflict) dead = true;
-                else { index_choice(ix, B, table, n_live, lane, kind, lit); continue; }
+                if (!conflict) {
+                    index_choice<kPlain>(ix, B, table, n_live, lane, kind, lit);
+                    if (!kPlain && lit == 0) { ++nodes; verdict = 1; break; }   // choice()==0 (only with a {0,0,0} root clause)
+                    continue;
+                }
             }
             // Backtrack: pop to the deepest decision whose LA sibling is still pending.
             __syncwarp();
@@ -904,7 +1023,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
             __syncwarp();
             if (lane == 0) {
                 pend[pos >> 5] &= ~(1u << (pos & 31));
-                trail[pos] = (short)(-trail[pos]);   // -i -> +i : now the LA sibling
+                p.trails[tbase + (unsigned)(pos)] = (short)(-p.trails[tbase + (unsigned)(pos)]);   // -i -> +i : now the LA sibling
             }
             ntrail = pos + 1;
             --npend;
@@ -914,13 +1033,13 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
                 __syncwarp();
                 __threadfence_block();
                 slot_copy(B, snap + (size_t)k * ix.slot_words, ix.slot_words, lane);
-                const int la = (int)trail[pos];
+                const int la = (int)p.trails[tbase + (unsigned)(pos)];
                 const int n_before = __shfl_sync(kFullMask, snap_n, k);
                 __syncwarp();
                 if (lane == 0) table_set(table, la);
                 bool conflict;
-                n_live = index_assign<true>(ix, B, n_before, la, conflict, lane);   // open and non-empty: it was left pending
-                index_choice(ix, B, table, n_live, lane, kind, lit);
+                n_live = index_assign<true, kPlain>(ix, B, n_before, la, conflict, lane);   // open and non-empty: it was left pending
+                index_choice<kPlain>(ix, B, table, n_live, lane, kind, lit);
                 continue;
             }
             snap_low = min(snap_low, npend);   // siblings pushed from here on have intact snapshots again
@@ -928,13 +1047,13 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
             __syncwarp();
             __threadfence_block();
             for (int j = lane; j < ntrail; j += 32) {
-                const int l = trail[j];
+                const int l = p.trails[tbase + (unsigned)(j)];
                 const unsigned v = (unsigned)(l < 0 ? -l : l);
                 atomicOr(&table[v >> 4], (l > 0 ? 1u : 2u) << ((v & 15u) * 2u));
             }
             __syncwarp();
             n_live = index_rebuild(ix, B, table, lane);
-            index_choice(ix, B, table, n_live, lane, kind, lit);
+            index_choice<kPlain>(ix, B, table, n_live, lane, kind, lit);
         }
         if (verdict == 1) {
             int park = 0;
@@ -954,7 +1073,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
                 __syncwarp();
                 __threadfence_block();
                 int32_t* out = p.models + (size_t)gwarp * p.trail_cap;
-                for (int j = lane; j < ntrail; j += 32) out[j] = (int32_t)trail[j];
+                for (int j = lane; j < ntrail; j += 32) out[j] = (int32_t)p.trails[tbase + (unsigned)(j)];
                 if (lane == 0) { p.model_sub[gwarp] = q; p.model_len[gwarp] = ntrail; }
             }
         }

@@ -143,12 +143,12 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
                 t = lit;                            // the other branch falsifies the unit clause
             } else {
                 bool la_conf, ra_conf;
-                const int la_n = index_assign<false>(ix, S, n_live, v, la_conf, lane);
+                int la_n, ra_n;
+                index_classify(ix, S, n_live, v, la_n, la_conf, ra_n, ra_conf, lane);
                 if (la_n == 0) {                    // LA empty wins first (NDP:843-850)
                     if (lane == 0) chain[nchain] = (short)v;
                     ++nchain; outcome = SPLIT_LEAF; break;
                 }
-                const int ra_n = index_assign<false>(ix, S, n_live, -v, ra_conf, lane);
                 if (ra_n == 0) {                    // NDP:863-870
                     if (lane == 0) chain[nchain] = (short)(-v);
                     ++nchain; outcome = SPLIT_LEAF; break;

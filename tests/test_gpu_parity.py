@@ -150,6 +150,48 @@ def test_dfs_golden_small_and_medium(nd, oracle, golden, cnf_text):
     assert n >= 15
 
 
+def test_dfs_generic_kernel_on_generated_cnfs(nd, golden, oracle, cnf_text, monkeypatch):
+    """Generated factoring CNFs take the kernels' kPlain instantiation (B[2] summary, no {0,0,0} clause, no
+    variable twice in a clause).  NDP_NO_PLAIN forces the generic instantiation on the same inputs: the
+    golden verdicts, node and clause-evaluation counts must not move."""
+    monkeypatch.setenv("NDP_NO_PLAIN", "1")
+    n = 0
+    for c in golden["cases"]:
+        if "verdict" not in c or c["bits"] not in (12, 16, 20):
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        r = fr.dfs_shard()
+        key = (c["cnf"], c["mode"], c["value"])
+        assert r["verdict"].tolist() == c["verdict"], key
+        assert r["nodes"].tolist() == c["nodes"] and r["evals"].tolist() == c["clause_evals"], key
+        fr.free()
+        n += 1
+    assert n >= 8
+
+
+def test_bfs_level_wider_than_the_device_loop_can_hold(nd, golden, oracle, cnf_text, monkeypatch):
+    """A level with more nodes per CTA than the persistent BFS kernel's shared scan arrays hold (2048 x SMs:
+    -q above ~300k) must go through the per-level kernels instead of relaunching the device loop for ever
+    (round-1 advisor finding).  NDP_PERSIST_BLOCK_NODES lowers the limit so small inputs take that path."""
+    monkeypatch.setenv("NDP_PERSIST_BLOCK_NODES", "1")
+    n = 0
+    for c in golden["cases"]:
+        if c["cnf"] not in ("rsaFACT-16bit", "prime-16bit", "rsaFACT-24bit") or c["size"] < 8:
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        key = (c["cnf"], c["mode"], c["value"])
+        assert (fr.iterations, fr.task_count, len(fr)) == (c["iterations"], c["task_count"], c["size"]), key
+        assert util_cnf.frontier_digest(gpu_frontier_list(fr)) == c["frontier_sha256"], key
+        assert fr.bfs_stats()["clause_evals"] == c["bfs_clause_evals"], key
+        fr.free()
+        n += 1
+    assert n >= 6
+
+
 def test_dfs_random_small(nd, oracle):
     rng = np.random.default_rng(99)
     sat = 0
