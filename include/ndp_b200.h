@@ -168,6 +168,39 @@ int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early
                          int32_t* model, size_t model_cap, size_t* model_len, uint64_t* nodes, uint64_t* evals,
                          ndp_stats* stats);
 
+/* ---- piece-level sharing between processes (one process per GPU) ------------------------------
+ * The reference's dispatcher hands out one task per request, so no worker idles while tasks remain
+ * (NDP:1322-1346).  A static k mod world split of SUBPROBLEMS cannot do that when the frontier is narrow
+ * or its subproblems are heavy-tailed; these three calls share out PIECES instead.  Every rank holds the
+ * whole frontier (each ran the deterministic BFS, as every reference rank does, NDP:1651) and makes the
+ * SAME DFS-order cut of it into pieces (ndp_set_split policy, sized for world devices); rank r searches
+ * pieces r, r + world, ... -- tens of thousands of small units per rank, so the ranks finish together.
+ * Results are per-piece and fold back per subproblem with two tiny collectives the CALLER runs (the
+ * library holds no communicator):
+ *   ndp_dfs_pieces_begin  cut + search this rank's pieces.  first_model[k] (ndp_frontier_size entries) =
+ *                         lowest piece OF THIS RANK holding a model of subproblem k, UINT32_MAX if none.
+ *                         own / peers: early-exit words as in ndp_dfs_shard_shared (may be NULL / 0); inside
+ *                         a piece run a word holds the lowest PIECE index with a model.
+ *   -> MIN all-reduce of first_model over the ranks
+ *   ndp_dfs_pieces_fold   this rank's PARTIAL results given the job-wide first_model: verdict[k] (combine
+ *                         with MAX: UNSAT 0 < SAT 1 < NOT_RUN 2; SAT is reported by every rank), nodes[k] /
+ *                         evals[k] (combine with SUM: pieces up to the first model, the reference's counts),
+ *                         winner = lowest SAT subproblem (the same on every rank), and -- only on the rank that
+ *                         searched the winning piece, model_len = 0 elsewhere -- the model choices_k ++ DFS
+ *                         choices (final_choices_i of NDP:1430-1431).  stats->nodes / clause_evals: this
+ *                         rank's sums.
+ *   ndp_dfs_pieces_end    frees the run.
+ * A frontier wide enough for world devices is not cut: the pieces are the subproblems and the calls
+ * reduce to ndp_dfs_shard_shared(first = rank, stride = world).  world = 1 is valid. */
+typedef struct ndp_piece_run ndp_piece_run;
+int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_exit, ndp_exit_word* own,
+                         ndp_exit_word* const* peers, int n_peers, ndp_piece_run** run, uint32_t* first_model,
+                         ndp_stats* stats);
+int ndp_dfs_pieces_fold(ndp_piece_run* run, const uint32_t* first_model, uint8_t* verdict, uint64_t* nodes,
+                        uint64_t* evals, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                        ndp_stats* stats);
+void ndp_dfs_pieces_end(ndp_piece_run* run);
+
 /* Whole frontier on n_gpus devices of this process (static interleaved split k -> k mod n_gpus,
  * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1.  A frontier too
  * narrow for the devices (-d 12, -d 20: ONE subproblem) is first cut into DFS-order pieces on its home

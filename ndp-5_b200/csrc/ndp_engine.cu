@@ -1892,85 +1892,137 @@ int batch_core(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, si
 
 
 // Pieces of a split as a frontier of their own: element p = piece p (state slots in the split's arena,
-// no choices), so that batch_core can shard them over devices like subproblems.  Per-piece results are
-// then folded back per subproblem exactly as in dfs_on_device.
-int batch_over_pieces(ndp_frontier* f, const IndexRoot& ix, SplitRun& split, int n_gpus, int early_exit,
-                      uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
-                      ndp_stats* stats) {
+// no choices), so that batch_core / dfs_on_device can shard them over devices or ranks like subproblems.
+// Per-piece results are then folded back per subproblem exactly as in dfs_on_device.
+struct PieceSet {
+    std::unique_ptr<ndp_frontier> pf;                    // borrows the split's arena and the parent's root indexes
+    ndp_frontier* parent = nullptr;
+    std::vector<int32_t> orig;                           // [pieces] subproblem a piece belongs to
+    std::vector<unsigned long long> pre_n, pre_e;        // [pieces] split-interior nodes / evals charged to the piece
+    std::vector<unsigned long long> tail_n, tail_e;      // [subproblems] dead ends after the last piece
+    size_t np = 0;
+    // hand the borrowed parts back (the arena belongs to the split; root indexes built for new devices move to the parent)
+    void release() {
+        if (!pf) return;
+        pf->sbuf[0] = nullptr;
+        for (size_t i = pf->root_borrowed; i < pf->root_indexes.size(); ++i) parent->root_indexes.push_back(pf->root_indexes[i]);
+        pf->root_borrowed = pf->root_indexes.size();
+        pf.reset();
+    }
+    ~PieceSet() { release(); }
+};
+
+int make_piece_set(ndp_frontier* f, const IndexRoot& ix, SplitRun& split, PieceSet& ps) {
     const size_t n_sub = f->entries.size(), np = split.n_pieces;
     const SplitLevel& L = split.sp.lv[split.side];
-    if (winner) *winner = SIZE_MAX;
-    if (model_len) *model_len = 0;
-    std::vector<const unsigned*> h_ptr(std::max(np, (size_t)1));
-    std::vector<BfsNode> h_meta(std::max(np, (size_t)1));
-    std::vector<int32_t> h_orig(std::max(np, (size_t)1));
-    std::vector<unsigned long long> h_pre_n(std::max(np, (size_t)1)), h_pre_e(std::max(np, (size_t)1)), h_tail_n(n_sub), h_tail_e(n_sub);
+    ps.parent = f;
+    ps.np = np;
+    const size_t np1 = std::max(np, (size_t)1);
+    std::vector<const unsigned*> h_ptr(np1);
+    std::vector<BfsNode> h_meta(np1);
+    ps.orig.assign(np1, 0);
+    ps.pre_n.assign(np1, 0); ps.pre_e.assign(np1, 0);
+    ps.tail_n.assign(n_sub, 0); ps.tail_e.assign(n_sub, 0);
     CUDA_TRY(cudaSetDevice(f->device));
     if (np) {
         CUDA_TRY(cudaMemcpy(h_ptr.data(), L.ptr, np * sizeof(unsigned*), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(h_meta.data(), L.meta, np * sizeof(BfsNode), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(h_orig.data(), L.orig, np * 4, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(h_pre_n.data(), L.pre_nodes, np * 8, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(h_pre_e.data(), L.pre_evals, np * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ps.orig.data(), L.orig, np * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ps.pre_n.data(), L.pre_nodes, np * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ps.pre_e.data(), L.pre_evals, np * 8, cudaMemcpyDeviceToHost));
     }
-    CUDA_TRY(cudaMemcpy(h_tail_n.data(), split.sp.tail_nodes, n_sub * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h_tail_e.data(), split.sp.tail_evals, n_sub * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ps.tail_n.data(), split.sp.tail_nodes, n_sub * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ps.tail_e.data(), split.sp.tail_evals, n_sub * 8, cudaMemcpyDeviceToHost));
     // every surviving piece of the last level sits in the arena that level wrote (LEAF pieces have no slot)
     unsigned* arena = split.sp.sbuf[split.side];
-    std::unique_ptr<ndp_frontier> pf(new ndp_frontier);
+    ps.pf.reset(new ndp_frontier);
+    ndp_frontier* pf = ps.pf.get();
     pf->device = f->device;
     pf->max_var = f->max_var;
     pf->states = true;
     pf->has_root = true;
     pf->root_c3 = f->root_c3;
-    pf->root_indexes = f->root_indexes;      // same root: share the per-device indexes already built ...
+    pf->root_indexes = f->root_indexes;      // same root: share the per-device indexes already built
     pf->root_borrowed = pf->root_indexes.size();
     pf->host_tree_ready = true;
     pf->sbuf[0] = arena;
     pf->scap_slots[0] = 0;
+    pf->entries.reserve(np);
     for (size_t pc = 0; pc < np; ++pc) {
         uint32_t slot = 0;
         if (h_ptr[pc]) {
             const size_t off = (size_t)(h_ptr[pc] - arena);
-            if (h_ptr[pc] < arena || off % (size_t)ix.slot_words) { pf->sbuf[0] = nullptr; return fail(NDP_E_CUDA, "piece slot outside the split arena"); }
+            if (h_ptr[pc] < arena || off % (size_t)ix.slot_words) return fail(NDP_E_CUDA, "piece slot outside the split arena");
             slot = (uint32_t)(off / (size_t)ix.slot_words);
         }
         pf->entries.push_back(Entry{0, slot, h_meta[pc].n, -1, h_meta[pc].kind, h_meta[pc].lit});
     }
+    return NDP_OK;
+}
+
+// choices_k ++ the split's path to piece `pwin` of subproblem `win` (the caller appends the DFS tail)
+int model_prefix(ndp_frontier* f, SplitRun& split, size_t win, size_t pwin, std::vector<int32_t>& m, ndp_stats* stats) {
+    int rc = frontier_choices(f, win, m);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(f->device));
+    const SplitLevel& L = split.sp.lv[split.side];
+    const int cap = std::max(f->max_var, 1) + 8;
+    int32_t leaf = -1, start = 0;
+    CUDA_TRY(cudaMemcpy(&leaf, L.tnode + pwin, 4, cudaMemcpyDeviceToHost));
+    DevBuf d_out, d_start;
+    CUDA_TRY(dev_alloc(&d_out.p, (size_t)cap * 4));
+    CUDA_TRY(dev_alloc(&d_start.p, 4));
+    split_path_kernel<<<1, 1>>>(split.sp.t_parent, split.sp.t_lit, split.sp.t_seg_off, split.sp.t_seg_len, split.sp.log,
+                                leaf, d_out.as<int32_t>(), cap, d_start.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(&start, d_start.p, 4, cudaMemcpyDeviceToHost));
+    if (start < 0) return fail(NDP_E_CUDA, "split path longer than the variable count");
+    std::vector<int32_t> path((size_t)(cap - start));
+    if (!path.empty())
+        CUDA_TRY(cudaMemcpy(path.data(), d_out.as<int32_t>() + start, path.size() * 4, cudaMemcpyDeviceToHost));
+    m.insert(m.end(), path.begin(), path.end());
+    if (stats) { stats->launches += 1; stats->d2h_bytes += 8 + path.size() * 4; }
+    return NDP_OK;
+}
+
+int batch_over_pieces(ndp_frontier* f, const IndexRoot& ix, SplitRun& split, int n_gpus, int early_exit,
+                      uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                      ndp_stats* stats) {
+    const size_t n_sub = f->entries.size(), np = split.n_pieces;
+    if (winner) *winner = SIZE_MAX;
+    if (model_len) *model_len = 0;
+    PieceSet ps;
+    int rc = make_piece_set(f, ix, split, ps);
+    if (rc) return rc;
     std::vector<uint8_t> pv(std::max(np, (size_t)1), NDP_NOT_RUN);
     std::vector<uint64_t> pn(std::max(np, (size_t)1), 0), pe(std::max(np, (size_t)1), 0);
     std::vector<int32_t> tail(model_cap ? model_cap : 1);
     size_t pwin = SIZE_MAX, tail_len = 0;
     ndp_stats st;
     memset(&st, 0, sizeof st);
-    int rc = NDP_OK;
-    if (np) rc = batch_core(pf.get(), n_gpus, early_exit, pv.data(), &pwin, tail.data(), tail.size(), &tail_len, pn.data(),
+    if (np) rc = batch_core(ps.pf.get(), n_gpus, early_exit, pv.data(), &pwin, tail.data(), tail.size(), &tail_len, pn.data(),
                             pe.data(), &st);
-    pf->sbuf[0] = nullptr;   // the arena belongs to the split
-    for (size_t i = pf->root_borrowed; i < pf->root_indexes.size(); ++i)   // ... and keep the ones built for new devices
-        f->root_indexes.push_back(pf->root_indexes[i]);
-    pf->root_borrowed = pf->root_indexes.size();
-    pf.reset();
+    ps.release();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(f->device));
     // fold the pieces back: first piece with a model decides the subproblem; counters as in dfs_on_device
     std::vector<size_t> first_sat(n_sub, SIZE_MAX);
     for (size_t pc = 0; pc < np; ++pc)
-        if (pv[pc] == NDP_SAT && first_sat[(size_t)h_orig[pc]] == SIZE_MAX) first_sat[(size_t)h_orig[pc]] = pc;
+        if (pv[pc] == NDP_SAT && first_sat[(size_t)ps.orig[pc]] == SIZE_MAX) first_sat[(size_t)ps.orig[pc]] = pc;
     std::vector<uint8_t> sub_v(n_sub, NDP_UNSAT);
     std::vector<unsigned long long> sub_n(n_sub, 0), sub_e(n_sub, 0);
     for (size_t pc = 0; pc < np; ++pc) {
-        const size_t o = (size_t)h_orig[pc];
+        const size_t o = (size_t)ps.orig[pc];
         if (first_sat[o] != SIZE_MAX && pc > first_sat[o]) continue;
-        sub_n[o] += h_pre_n[pc] + pn[pc];
-        sub_e[o] += h_pre_e[pc] + pe[pc];
+        sub_n[o] += ps.pre_n[pc] + pn[pc];
+        sub_e[o] += ps.pre_e[pc] + pe[pc];
         if (pv[pc] == NDP_NOT_RUN && sub_v[o] == NDP_UNSAT) sub_v[o] = NDP_NOT_RUN;
     }
     size_t win = SIZE_MAX;
     uint64_t tn = 0, te = 0;
     for (size_t o = 0; o < n_sub; ++o) {
         if (first_sat[o] != SIZE_MAX) sub_v[o] = NDP_SAT;
-        else if (sub_v[o] == NDP_UNSAT) { sub_n[o] += h_tail_n[o]; sub_e[o] += h_tail_e[o]; }
+        else if (sub_v[o] == NDP_UNSAT) { sub_n[o] += ps.tail_n[o]; sub_e[o] += ps.tail_e[o]; }
         if (verdict) verdict[o] = sub_v[o];
         tn += sub_n[o]; te += sub_e[o];
         if (sub_v[o] == NDP_SAT && win == SIZE_MAX) win = o;
@@ -1981,23 +2033,7 @@ int batch_over_pieces(ndp_frontier* f, const IndexRoot& ix, SplitRun& split, int
     if (win != SIZE_MAX && (model || model_len)) {
         // choices_k ++ the split's path to the winning piece ++ what the device that searched it appended
         std::vector<int32_t> m;
-        if ((rc = frontier_choices(f, win, m))) return rc;
-        CUDA_TRY(cudaSetDevice(f->device));
-        const int cap = std::max(f->max_var, 1) + 8;
-        int32_t leaf = -1, start = 0;
-        CUDA_TRY(cudaMemcpy(&leaf, L.tnode + pwin, 4, cudaMemcpyDeviceToHost));
-        DevBuf d_out, d_start;
-        CUDA_TRY(dev_alloc(&d_out.p, (size_t)cap * 4));
-        CUDA_TRY(dev_alloc(&d_start.p, 4));
-        split_path_kernel<<<1, 1>>>(split.sp.t_parent, split.sp.t_lit, split.sp.t_seg_off, split.sp.t_seg_len, split.sp.log,
-                                    leaf, d_out.as<int32_t>(), cap, d_start.as<int32_t>());
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpy(&start, d_start.p, 4, cudaMemcpyDeviceToHost));
-        if (start < 0) return fail(NDP_E_CUDA, "split path longer than the variable count");
-        std::vector<int32_t> path((size_t)(cap - start));
-        if (!path.empty())
-            CUDA_TRY(cudaMemcpy(path.data(), d_out.as<int32_t>() + start, path.size() * 4, cudaMemcpyDeviceToHost));
-        m.insert(m.end(), path.begin(), path.end());
+        if ((rc = model_prefix(f, split, win, pwin, m, stats))) return rc;
         m.insert(m.end(), tail.begin(), tail.begin() + tail_len);
         if (model_len) *model_len = m.size();
         if (model) {
@@ -2148,6 +2184,153 @@ int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early
         }
     }
     return NDP_OK;
+}
+
+// ---- piece-level sharing between processes ---------------------------------------------------
+struct ndp_piece_run {
+    ndp_frontier* f = nullptr;
+    size_t rank = 0, world = 1, n_sub = 0, np = 0;
+    bool cut = false;                     // false: the pieces ARE the subproblems (frontier wide enough)
+    SplitRun split;                       // owns the split's arenas (cut == true)
+    PieceSet ps;
+    std::vector<uint8_t> pv;              // [pieces] verdicts of this rank's pieces (others NDP_NOT_RUN / untouched)
+    std::vector<uint64_t> pn, pe;         // [pieces] own nodes / evals
+    size_t pwin = SIZE_MAX;               // lowest own piece with a model
+    std::vector<int32_t> tail;            // the DFS choices of pwin
+};
+
+int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_exit, ndp_exit_word* own,
+                         ndp_exit_word* const* peers, int n_peers, ndp_piece_run** run_out, uint32_t* first_model,
+                         ndp_stats* stats) {
+    if (!f || !run_out) return fail(NDP_E_INVALID, "null argument");
+    *run_out = nullptr;
+    if (world == 0 || rank >= world) return fail(NDP_E_INVALID, "rank must be < world");
+    if (own && own->imported) return fail(NDP_E_INVALID, "own must be a word this process created");
+    if (n_peers < 0 || n_peers > 7 || (n_peers && (!peers || !own))) return fail(NDP_E_INVALID, "0..7 peer words (with own)");
+    int rc = check_device();
+    if (rc) return rc;
+    if (own && own->device != f->device) return fail(NDP_E_INVALID, "the exit word lives on another device than the frontier");
+    if (stats) memset(stats, 0, sizeof *stats);
+    std::unique_ptr<ndp_piece_run> run(new ndp_piece_run);
+    run->f = f; run->rank = rank; run->world = world;
+    run->n_sub = f->entries.size();
+    if (run->n_sub > 0xfffffff0ull) return fail(NDP_E_UNSUPPORTED, "frontier larger than the 32-bit piece index");
+    const double t0 = now_ms();
+    // the cut: identical on every rank (same frontier, same device model, same world)
+    const IndexRoot* ix = nullptr;
+    if (engine_uses_index(f) && run->n_sub) {
+        ndp_frontier::IndexReplica* rep = nullptr;
+        if ((rc = build_index_replica(f, f->device, 0, 1, &ix, &rep))) return rc;
+        CUDA_TRY(cudaSetDevice(f->device));
+        IndexLaunchPlan iplan;
+        if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
+        const size_t n_warps = (size_t)iplan.grid * iplan.warps_per_cta * world;
+        const size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive);
+        if (target > run->n_sub) {
+            if ((rc = run_split(f->device, *ix, *rep, target, run->split, stats))) return rc;
+            run->cut = run->split.active;
+        }
+    }
+    ndp_frontier* pf = f;
+    if (run->cut) {
+        if ((rc = make_piece_set(f, *ix, run->split, run->ps))) return rc;
+        pf = run->ps.pf.get();
+        run->np = run->split.n_pieces;
+    } else {
+        run->np = run->n_sub;
+    }
+    const double split_ms = now_ms() - t0;
+    const size_t np1 = std::max(run->np, (size_t)1);
+    run->pv.assign(np1, NDP_NOT_RUN);
+    run->pn.assign(np1, 0);
+    run->pe.assign(np1, 0);
+    std::vector<unsigned long long*> all;
+    if (own) {
+        all.push_back(own->ptr);
+        for (int i = 0; i < n_peers; ++i) {
+            if (!peers[i]) return fail(NDP_E_INVALID, "peer word is null");
+            all.push_back(peers[i]->ptr);
+        }
+    }
+    ndp_stats st;
+    memset(&st, 0, sizeof st);
+    if (run->np) {
+        rc = dfs_on_device(pf, f->device, rank, world, early_exit, own ? own->ptr : nullptr, own ? all.data() : nullptr,
+                           (int)all.size(), ~0ull, run->pv.data(), &run->pwin, &run->tail, run->pn.data(), run->pe.data(), &st);
+        if (rc) return rc;
+    }
+    if (stats) {
+        stats->kernel_ms += st.kernel_ms + (run->cut ? split_ms : 0.0);   // the cut is part of the search
+        stats->launches += st.launches; stats->h2d_bytes += st.h2d_bytes; stats->d2h_bytes += st.d2h_bytes;
+        stats->rebuilds += st.rebuilds;
+    }
+    if (first_model) {
+        for (size_t o = 0; o < run->n_sub; ++o) first_model[o] = 0xffffffffu;
+        for (size_t pc = rank; pc < run->np; pc += world)
+            if (run->pv[pc] == NDP_SAT) {
+                const size_t o = run->cut ? (size_t)run->ps.orig[pc] : pc;
+                if (first_model[o] == 0xffffffffu) first_model[o] = (uint32_t)pc;
+            }
+    }
+    *run_out = run.release();
+    return NDP_OK;
+}
+
+int ndp_dfs_pieces_fold(ndp_piece_run* run, const uint32_t* first_model, uint8_t* verdict, uint64_t* nodes,
+                        uint64_t* evals, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
+                        ndp_stats* stats) {
+    if (!run || !first_model) return fail(NDP_E_INVALID, "null argument");
+    if (model_len) *model_len = 0;
+    if (winner) *winner = SIZE_MAX;
+    const size_t n_sub = run->n_sub, np = run->np, rank = run->rank, world = run->world;
+    std::vector<uint8_t> sub_v(n_sub, NDP_UNSAT);
+    std::vector<uint64_t> sub_n(n_sub, 0), sub_e(n_sub, 0);
+    for (size_t pc = rank; pc < np; pc += world) {
+        const size_t o = run->cut ? (size_t)run->ps.orig[pc] : pc;
+        if (first_model[o] != 0xffffffffu && pc > (size_t)first_model[o]) continue;   // the reference stops at the first model
+        sub_n[o] += run->pn[pc] + (run->cut ? run->ps.pre_n[pc] : 0ull);
+        sub_e[o] += run->pe[pc] + (run->cut ? run->ps.pre_e[pc] : 0ull);
+        if (run->pv[pc] == NDP_NOT_RUN) sub_v[o] = NDP_NOT_RUN;
+    }
+    size_t win = SIZE_MAX;
+    uint64_t tn = 0, te = 0;
+    for (size_t o = 0; o < n_sub; ++o) {
+        if (first_model[o] != 0xffffffffu) {
+            sub_v[o] = NDP_SAT;                                   // on every rank: the word is job-wide
+            if (win == SIZE_MAX) win = o;
+        } else if (run->cut && o % world == rank) {               // dead ends after the last piece: one rank adds them
+            sub_n[o] += run->ps.tail_n[o];
+            sub_e[o] += run->ps.tail_e[o];
+        }
+        if (verdict) verdict[o] = sub_v[o];
+        if (nodes) nodes[o] = sub_n[o];
+        if (evals) evals[o] = sub_e[o];
+        tn += sub_n[o]; te += sub_e[o];
+    }
+    if (stats) { stats->nodes = tn; stats->clause_evals = te; }
+    if (winner) *winner = win;
+    if (win != SIZE_MAX && (size_t)first_model[win] % world == rank && (model || model_len)) {
+        // this rank searched the winning piece: choices_k ++ the cut's path to it ++ its DFS choices
+        const size_t pwin = (size_t)first_model[win];
+        if (run->pwin != pwin) return fail(NDP_E_CUDA, "piece winner disagrees with the per-subproblem fold");
+        std::vector<int32_t> m;   // (without a cut dfs_on_device already returned choices_k ++ DFS choices)
+        int rc;
+        if (run->cut && (rc = model_prefix(run->f, run->split, win, pwin, m, stats))) return rc;
+        m.insert(m.end(), run->tail.begin(), run->tail.end());
+        if (model_len) *model_len = m.size();
+        if (model) {
+            if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            memcpy(model, m.data(), m.size() * sizeof(int32_t));
+        }
+    }
+    return NDP_OK;
+}
+
+void ndp_dfs_pieces_end(ndp_piece_run* run) {
+    if (!run) return;
+    cudaSetDevice(run->f->device);
+    run->ps.release();
+    delete run;
 }
 
 int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,

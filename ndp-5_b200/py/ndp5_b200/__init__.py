@@ -22,6 +22,7 @@ _i32p = C.POINTER(C.c_int32)
 _szp = C.POINTER(C.c_size_t)
 _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
 
 
 class NdpError(RuntimeError):
@@ -74,6 +75,12 @@ def _load():
         "ndp_dfs_shard_shared": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
                                            C.POINTER(C.c_void_p), C.c_int, _u8p, _szp, _i32p, C.c_size_t, _szp,
                                            _u64p, _u64p, C.POINTER(Stats)]),
+        "ndp_dfs_pieces_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
+                                           C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), _u32p,
+                                           C.POINTER(Stats)]),
+        "ndp_dfs_pieces_fold": (C.c_int, [C.c_void_p, _u32p, _u8p, _u64p, _u64p, _szp, _i32p, C.c_size_t, _szp,
+                                          C.POINTER(Stats)]),
+        "ndp_dfs_pieces_end": (None, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -227,6 +234,19 @@ class Frontier:
         return dict(verdict=verdict[:n], winner=None if winner.value == SIZE_MAX else winner.value,
                     model=model[:mlen.value].copy(), nodes=nodes[:n], evals=evals[:n], stats=st.as_dict())
 
+    def dfs_pieces(self, rank=0, world=1, early_exit=False, own=None, peers=()):
+        """ndp_dfs_pieces_begin: cut the frontier into DFS-order pieces (the same cut on every rank) and search
+        pieces rank, rank + world, ...  Returns a PieceRun; combine with shard.fold_piece_runs (or call
+        .fold(first_model) yourself after a MIN all-reduce of .first_model)."""
+        n = len(self)
+        first_model = np.full(max(n, 1), 0xffffffff, dtype=np.uint32)
+        h = C.c_void_p(None)
+        st = Stats()
+        arr = (C.c_void_p * max(len(peers), 1))(*[p.h for p in peers])
+        _check(lib.ndp_dfs_pieces_begin(self.h, rank, world, int(early_exit), own.h if own is not None else None, arr,
+                                        len(peers), C.byref(h), first_model.ctypes.data_as(_u32p), C.byref(st)))
+        return PieceRun(h, n, first_model[:n], st.as_dict())
+
     def dfs_batch(self, n_gpus=1, early_exit=False, model_cap=1 << 16):
         n = len(self)
         verdict = np.full(max(n, 1), NOT_RUN, dtype=np.uint8)
@@ -253,6 +273,44 @@ class Frontier:
     def free(self):
         if self.h:
             lib.ndp_frontier_free(self.h)
+            self.h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PieceRun:
+    """Owner of an ndp_piece_run handle (this rank's share of a piece-level search)."""
+
+    def __init__(self, handle, n, first_model, stats):
+        self.h, self.n, self.first_model, self.stats = handle, n, first_model, stats
+
+    def fold(self, first_model, model_cap=1 << 16):
+        """ndp_dfs_pieces_fold: this rank's partial per-subproblem results given the job-wide first_model."""
+        n = self.n
+        fm = np.ascontiguousarray(np.asarray(first_model, dtype=np.uint32))
+        if fm.size < max(n, 1):
+            fm = np.concatenate([fm, np.full(max(n, 1) - fm.size, 0xffffffff, dtype=np.uint32)])
+        verdict = np.zeros(max(n, 1), dtype=np.uint8)
+        nodes = np.zeros(max(n, 1), dtype=np.uint64)
+        evals = np.zeros(max(n, 1), dtype=np.uint64)
+        winner = C.c_size_t(SIZE_MAX)
+        model = np.zeros(model_cap, dtype=np.int32)
+        mlen = C.c_size_t(0)
+        st = Stats()
+        _check(lib.ndp_dfs_pieces_fold(self.h, fm.ctypes.data_as(_u32p), verdict.ctypes.data_as(_u8p),
+                                       nodes.ctypes.data_as(_u64p), evals.ctypes.data_as(_u64p), C.byref(winner),
+                                       model.ctypes.data_as(_i32p), model_cap, C.byref(mlen), C.byref(st)))
+        return dict(verdict=verdict[:n], nodes=nodes[:n], evals=evals[:n],
+                    winner=None if winner.value == SIZE_MAX else winner.value, model=model[:mlen.value].copy(),
+                    stats=dict(self.stats, nodes=st.nodes, clause_evals=st.clause_evals))
+
+    def free(self):
+        if self.h:
+            lib.ndp_dfs_pieces_end(self.h)
             self.h = C.c_void_p(None)
 
     def __del__(self):

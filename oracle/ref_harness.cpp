@@ -156,6 +156,17 @@ int ref_dfs(const int32_t* c3, size_t n, int first_assignment, int32_t* model, s
 // without the MPI messages.  early_exit!=0 mirrors NDP:1297-1303/1447: the job ends at the
 // first reported model.  verdict[k]: 0 UNSAT, 1 SAT, 2 not run.  Returns wall seconds.
 // winner/model: lowest-index SAT subproblem's full model = choices_k ++ dfs choices (NDP:1430-1431).
+// Worker time each subproblem took in the last ref_dfs_frontier (0 for those not run); returns the sum.
+static std::vector<double> g_last_busy;
+double ref_last_busy_seconds(double* per_subproblem, size_t cap) {
+    double sum = 0;
+    for (size_t k = 0; k < g_last_busy.size(); ++k) {
+        sum += g_last_busy[k];
+        if (per_subproblem && k < cap) per_subproblem[k] = g_last_busy[k];
+    }
+    return sum;
+}
+
 double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int early_exit, uint8_t* verdict,
                         long* winner, int32_t* model, size_t model_cap, size_t* model_len, long* nodes_out) {
     Frontier& f = *static_cast<Frontier*>(h);
@@ -164,7 +175,7 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
     if (workers < 1) workers = 1;
     const size_t model_ints = 1u << 22;
     struct Shared { std::atomic<long> next; std::atomic<long> found; std::atomic<long> model_off; };
-    size_t bytes = sizeof(Shared) + count + 64 + model_ints * sizeof(int32_t) + count * sizeof(long) * 3;
+    size_t bytes = sizeof(Shared) + count + 64 + model_ints * sizeof(int32_t) + count * sizeof(long) * 3 + count * sizeof(double) + 16;
     char* mem = (char*)mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     Shared* sh = new (mem) Shared;
     sh->next = 0; sh->found = 0; sh->model_off = 0;
@@ -173,6 +184,7 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
     long* moff = (long*)(mem + voff);            // per subproblem: offset, len into models
     long* ncount = moff + 2 * count;             // per subproblem: DFS loop iterations (prof build) or -1
     int32_t* models = (int32_t*)(mem + voff + count * sizeof(long) * 3);
+    double* busy = (double*)(mem + ((voff + count * sizeof(long) * 3 + model_ints * sizeof(int32_t) + 15) & ~size_t(15)));   // per subproblem: seconds
     memset(v, 2, count);
     double t0 = now_s();
     std::vector<pid_t> pids;
@@ -184,7 +196,9 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
                 long k = sh->next.fetch_add(1);
                 if (k >= (long)count) break;
                 long n_before = dfs_node_count();
+                const double tk = now_s();
                 auto res = Satisfy_iterative(f[first_k + k].first, true);
+                busy[k] = now_s() - tk;
                 ncount[k] = n_before < 0 ? -1 : dfs_node_count() - n_before;
                 if (!res.empty()) {
                     const auto& ch = f[first_k + k].second;
@@ -219,6 +233,8 @@ double ref_dfs_frontier(void* h, size_t first_k, size_t count, int workers, int 
     if (t_end == 0) t_end = now_s();
     long win = -1;
     for (size_t k = 0; k < count; ++k) if (v[k] == 1) { win = (long)k; break; }
+    g_last_busy.assign(count, 0.0);
+    for (size_t k = 0; k < count; ++k) if (v[k] != 2) g_last_busy[k] = busy[k];
     if (verdict) memcpy(verdict, v, count);
     if (nodes_out) for (size_t k = 0; k < count; ++k) nodes_out[k] = v[k] == 2 ? 0 : ncount[k];
     if (winner) *winner = win < 0 ? -1 : (long)first_k + win;

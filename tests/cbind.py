@@ -187,6 +187,13 @@ class RefLib(_Common):
         return dict(seconds=sec, verdict=verdict[:count].copy(), winner=winner.value, model=model[:ml.value].copy(),
                     nodes=nodes[:count].copy())
 
+    def last_busy_seconds(self, count):
+        """Worker seconds each subproblem of the last dfs_frontier call took (0 for those not run)."""
+        f = self._fn("last_busy_seconds", C.c_double, [C.POINTER(C.c_double), C.c_size_t])
+        out = np.zeros(max(count, 1), dtype=np.float64)
+        f(out.ctypes.data_as(C.POINTER(C.c_double)), count)
+        return out[:count]
+
     def frontier_from_arrays(self, items):
         f = self._fn("frontier_from_arrays", C.c_void_p, [_i32p, _szp, _i32p, _szp, C.c_size_t])
         cl_off, ch_off = [0], [0]

@@ -153,3 +153,48 @@ def test_split_32bit_q1024_counts(nd, oracle, golden, cnf_text):
         if c["winner"] >= 0:
             assert r["winner"] == c["winner"] and r["model"].tolist() == c["sat"][str(c["winner"])]["model"]
         fr.free()
+
+
+def _emulate_ranks(fr, world, early_exit=False):
+    """ndp_dfs_pieces_* as `world` ranks would call it, one after the other on this GPU; the collectives
+    (MIN of first_model, MAX of verdicts, SUM of counters) are numpy here."""
+    runs = [fr.dfs_pieces(rank=r, world=world, early_exit=early_exit) for r in range(world)]
+    fm = np.minimum.reduce([run.first_model for run in runs])
+    parts = [run.fold(fm) for run in runs]
+    verdict = np.maximum.reduce([p["verdict"] for p in parts])
+    nodes = np.sum([p["nodes"] for p in parts], axis=0, dtype=np.uint64)
+    evals = np.sum([p["evals"] for p in parts], axis=0, dtype=np.uint64)
+    winners = {p["winner"] for p in parts}
+    assert len(winners) == 1, "every rank must name the same winner"
+    models = [p["model"] for p in parts if p["model"].size]
+    for run in runs:
+        run.free()
+    return verdict, nodes, evals, winners.pop(), models
+
+
+def test_piece_runs_between_ranks_golden(nd, oracle, golden, cnf_text):
+    """Piece-level sharing between processes (ndp_dfs_pieces_begin / fold): whatever the cut and the number
+    of ranks, the folded per-subproblem verdicts, node / clause-evaluation counts, the winner and its model are
+    the reference's; exactly one rank returns the model."""
+    n = 0
+    for c in golden["cases"]:
+        if "verdict" not in c or c["bits"] > 20:
+            continue
+        A = oracle.parse(cnf_text(c["cnf"]))
+        D, ovr, Q = util_cnf.settings_for(c["mode"], c["value"])
+        fr = nd.bfs(A, D, ovr, Q)
+        for target, world in [(0, 1), (0, 2), (0, 3), (50, 2), (700, 3), (5000, 8), ("auto", 4)]:
+            nd.set_split(target)
+            key = (c["cnf"], c["mode"], c["value"], target, world)
+            verdict, nodes, evals, winner, models = _emulate_ranks(fr, world)
+            assert verdict.tolist() == c["verdict"], key
+            assert nodes.tolist() == c["nodes"], key
+            assert evals.tolist() == c["clause_evals"], key
+            if c["winner"] >= 0:
+                assert winner == c["winner"], key
+                assert len(models) == 1 and models[0].tolist() == c["sat"][str(c["winner"])]["model"], key
+            else:
+                assert winner is None and not models, key
+        fr.free()
+        n += 1
+    assert n >= 10

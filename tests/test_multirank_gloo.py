@@ -86,6 +86,83 @@ def test_sharded_run_equals_single_rank(world, case, tmp_path, oracle, cnf_text)
             assert int(z["winner"]) == first[0] and z["model"].tolist() == first[1]
 
 
+class _OracleRun:
+    """What ndp5_b200.PieceRun is on the GPU box, restated with the oracle for a frontier that is not cut (the
+    pieces are the subproblems): this rank searched pieces rank, rank + world, ..."""
+
+    def __init__(self, orc, fr, rank, world):
+        self.n, self.rank, self.world = len(fr), rank, world
+        self.first_model = np.full(self.n, 0xffffffff, dtype=np.uint32)
+        self.res = {}
+        for k in range(rank, self.n, world):
+            r = orc.dfs(fr[k][0])
+            self.res[k] = (r, np.concatenate([fr[k][1], r["model"]]) if r["models"] else None)
+            if r["models"]:
+                self.first_model[k] = k
+
+    def fold(self, fm):
+        verdict = np.zeros(self.n, np.uint8)
+        nodes = np.zeros(self.n, np.uint64)
+        evals = np.zeros(self.n, np.uint64)
+        sat = np.nonzero(np.asarray(fm) != 0xffffffff)[0]
+        verdict[sat] = 1
+        for k, (r, _) in self.res.items():
+            nodes[k], evals[k] = r["nodes"], r["clause_evals"]
+        winner = int(sat[0]) if len(sat) else None
+        model = np.zeros(0, np.int32)
+        if winner is not None and int(fm[winner]) % self.world == self.rank:
+            model = self.res[winner][1]
+        return dict(verdict=verdict, nodes=nodes, evals=evals, winner=winner, model=model,
+                    stats=dict(nodes=int(nodes.sum()), clause_evals=int(evals.sum())))
+
+
+def _piece_worker(rank, world, port, case, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ndp_shard", os.path.join(ROOT, "ndp-5_b200", "py", "ndp5_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    import cbind
+    import gen_cnf
+    orc = cbind.OracleLib()
+    name, D, ovr, Q = case
+    fr = orc.bfs(orc.parse(gen_cnf.dimacs_text(*gen_cnf.NAMED[name])), D, ovr, Q)["frontier"]
+    out = shard.fold_piece_runs(dist, _OracleRun(orc, fr, rank, world), world)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), verdict=out["verdict"], nodes=out["nodes"], evals=out["evals"],
+             winner=-1 if out["winner"] is None else out["winner"],
+             model=np.zeros(0, np.int32) if out["winner"] is None else out["model"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", [("rsaFACT-16bit", 969, False, -1), ("prime-12bit", 0, True, 16)])
+def test_piece_fold_collectives(world, case, tmp_path, oracle, cnf_text):
+    """shard.fold_piece_runs (MIN of first_model, MAX of verdicts, SUM of counters, model from the rank that searched
+    the winning piece) over gloo: every rank ends with the single-rank verdicts, counters, winner and model."""
+    port = _free_port()
+    mp.spawn(_piece_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    name, D, ovr, Q = case
+    fr = oracle.bfs(oracle.parse(cnf_text(name)), D, ovr, Q)["frontier"]
+    want_v, want_n, want_e, first = [], [], [], None
+    for k, (cl, ch) in enumerate(fr):
+        r = oracle.dfs(cl)
+        want_v.append(1 if r["models"] else 0)
+        want_n.append(r["nodes"])
+        want_e.append(r["clause_evals"])
+        if r["models"] and first is None:
+            first = (k, np.concatenate([ch, r["model"]]).tolist())
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        assert z["verdict"].tolist() == want_v and z["nodes"].tolist() == want_n and z["evals"].tolist() == want_e
+        if first is None:
+            assert int(z["winner"]) == -1
+        else:
+            assert int(z["winner"]) == first[0] and z["model"].tolist() == first[1]
+
+
 def test_shard_indices_partition():
     import importlib.util
     spec = importlib.util.spec_from_file_location("ndp_shard", os.path.join(ROOT, "ndp-5_b200", "py", "ndp5_b200", "shard.py"))
