@@ -2224,8 +2224,16 @@ int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_e
         CUDA_TRY(cudaSetDevice(f->device));
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
+        // The job-wide cut is made by EVERY rank (replicated work), so it is coarse: enough pieces for the
+        // static deal piece -> rank to balance statistically (>= 4096 per rank), and only where cutting pays
+        // (split_target's test: shard starved or subproblems still deep).  Each rank then refines its own
+        // share down to pieces-per-warp granularity inside dfs_on_device -- in parallel, on its own data.
         const size_t n_warps = (size_t)iplan.grid * iplan.warps_per_cta * world;
-        const size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive);
+        size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive);
+        if (g_split < 0 && !getenv("NDP_SPLIT")) {            // automatic policy
+            const size_t coarse = (size_t)4096 * world;
+            target = (world > 1 && target > run->n_sub && coarse > run->n_sub) ? coarse : 0;
+        }
         if (target > run->n_sub) {
             if ((rc = run_split(f->device, *ix, *rep, target, run->split, stats))) return rc;
             run->cut = run->split.active;
