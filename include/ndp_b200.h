@@ -8,7 +8,11 @@
  *
  * Clause arrays are n x 3 row-major int32, exactly the layout flattenClauseSet produces
  * (NDP:1207-1215): literal 0 means "already false / padding" (CSP:37-39); a unit clause x is
- * {0,0,x} (NDP:632-634).
+ * {0,0,x} (NDP:632-634).  Variable ids are the caller's: any non-zero int32 except INT32_MIN, as sparse
+ * as the caller likes (Clause3 is `int l[3]`, CSP:37-39).  The kernels pack literals in 16-bit codes, so a
+ * CNF whose ids do not fit is renumbered inside the library (only variables that occur need a code) and
+ * every literal that leaves the library -- frontier clauses, choices, models -- is mapped back; the limit
+ * is 32766 DISTINCT variables (a 64-bit factoring CNF has 5952).
  *
  * There is no CPU fallback: every compute entry point fails with NDP_E_CUDA when no sm_100
  * device (or no CUDA driver) is present.
@@ -25,7 +29,7 @@ extern "C" {
 typedef enum ndp_status {
     NDP_OK = 0,
     NDP_E_INVALID = 1,      /* bad argument (null pointer, index out of range, ...) */
-    NDP_E_UNSUPPORTED = 2,  /* input outside what the kernels pack (|literal| > 32767, ...) */
+    NDP_E_UNSUPPORTED = 2,  /* input outside what the kernels hold (> 32766 DISTINCT variables, > 2^24 clauses, ...) */
     NDP_E_CUDA = 3,         /* CUDA runtime error / no usable device */
     NDP_E_NOMEM = 4         /* device arena or host allocation failed */
 } ndp_status;

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace ndp;
@@ -148,6 +149,11 @@ struct ndp_frontier {
     int32_t *d_tree_parent = nullptr, *d_tree_lit = nullptr;   // device copy of the tree (on `device`)
     size_t d_tree_count = 0;
     bool host_tree_ready = true;            // false while the tree lives only on the device
+    // ---- variable renumbering at the ABI (only when the caller's ids do not fit the 16-bit literal codes):
+    // the kernels see dense ids 1..V' in first-seen order, every literal that crosses the ABI is mapped back.
+    // choice() / resolution only ever look at |l| and sign(l) (NDP:654-781), so any bijection is exact.
+    std::vector<int32_t> ext_of;                       // dense variable -> caller's id ([0] unused); empty: identity
+    std::unordered_map<int32_t, int32_t> dense_of;     // caller's id -> dense variable
     // ---- root (BFS-born frontiers): what the index engine is built over
     bool has_root = false;
     std::vector<int32_t> root_c3;
@@ -297,6 +303,45 @@ bool pack_host(const int32_t* c3, size_t n, pclause* out, int& max_var) {
         out[k] = pack_clause(c3[3 * k], c3[3 * k + 1], c3[3 * k + 2]);
     }
     return true;
+}
+
+// ---- variable renumbering (see ndp_frontier::ext_of)
+bool needs_renumbering(const int32_t* lits, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (lits[i] > kMaxVar || lits[i] < -kMaxVar) return true;
+    return false;
+}
+// caller's literals -> dense literals.  Unknown variables get the next dense id (first-seen order).
+int map_in(ndp_frontier* f, const int32_t* lits, size_t n, int32_t* out) {
+    if (f->ext_of.empty()) f->ext_of.push_back(0);
+    for (size_t i = 0; i < n; ++i) {
+        const int32_t l = lits[i];
+        if (l == 0) { out[i] = 0; continue; }
+        if (l == INT32_MIN) return fail(NDP_E_UNSUPPORTED, "literal INT32_MIN has no negation");
+        const int32_t v = l < 0 ? -l : l;
+        auto it = f->dense_of.find(v);
+        int32_t d;
+        if (it != f->dense_of.end()) d = it->second;
+        else {
+            if (f->ext_of.size() > (size_t)kMaxVar)
+                return fail(NDP_E_UNSUPPORTED, "more than 32766 distinct variables (16-bit literal codes; state slots must fit shared memory)");
+            d = (int32_t)f->ext_of.size();
+            f->ext_of.push_back(v);
+            f->dense_of.emplace(v, d);
+        }
+        out[i] = l < 0 ? -d : d;
+    }
+    return NDP_OK;
+}
+// dense literals -> caller's literals, in place
+void map_out(const ndp_frontier* f, int32_t* lits, size_t n) {
+    if (f->ext_of.empty()) return;
+    for (size_t i = 0; i < n; ++i) {
+        const int32_t l = lits[i];
+        if (l == 0) continue;
+        const int32_t e = f->ext_of[(size_t)(l < 0 ? -l : l)];
+        lits[i] = l < 0 ? -e : e;
+    }
 }
 
 // Root index of a BFS-born frontier on `device`: packed root + merged occurrence lists.
@@ -604,6 +649,12 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
     f->device = g_device;
     f->stride = std::max(n_clauses, (size_t)1);
     std::vector<pclause> packed(f->stride);
+    std::vector<int32_t> dense;                   // ids beyond the 16-bit codes: renumber (sparse ids are fine, > 32766 distinct are not)
+    if (needs_renumbering(clauses3, 3 * n_clauses)) {
+        dense.resize(3 * n_clauses);
+        if ((rc = map_in(f.get(), clauses3, 3 * n_clauses, dense.data()))) return rc;
+        clauses3 = dense.data();
+    }
     if (!pack_host(clauses3, n_clauses, packed.data(), f->max_var))
         return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
     f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
@@ -997,6 +1048,7 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
             f->get_clauses[3 * c + 1] = l1;
             f->get_clauses[3 * c + 2] = l2;
         }
+        map_out(f, f->get_clauses.data(), (size_t)e.n * 3);
         if (clauses3) *clauses3 = f->get_clauses.data();
         if (n_clauses) *n_clauses = (size_t)e.n;
     }
@@ -1004,6 +1056,7 @@ int ndp_frontier_get(ndp_frontier* f, size_t k, const int32_t** clauses3, size_t
         int rc = ensure_host_tree(f);
         if (rc) return rc;
         f->choices_of(k, f->get_choices);
+        map_out(f, f->get_choices.data(), f->get_choices.size());
         if (f->get_choices.empty()) f->get_choices.reserve(1);
         if (choices) *choices = f->get_choices.data();
         if (n_choices) *n_choices = f->get_choices.size();
@@ -1032,11 +1085,20 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
     // stage in bounded chunks so a multi-GB resume does not double its footprint on the host
     const size_t chunk_slots = std::max<size_t>(1, ((size_t)64 << 20) / (stride * sizeof(pclause)));
     std::vector<pclause> stage(chunk_slots * stride);
+    const bool renumber = count && (needs_renumbering(clauses3 + 3 * clause_offsets[0], 3 * (clause_offsets[count] - clause_offsets[0])) ||
+                                    needs_renumbering(choices + choice_offsets[0], choice_offsets[count] - choice_offsets[0]));
+    std::vector<int32_t> dense;
     for (size_t k0 = 0; k0 < count; k0 += chunk_slots) {
         size_t k1 = std::min(count, k0 + chunk_slots);
         for (size_t k = k0; k < k1; ++k) {
             size_t n = clause_offsets[k + 1] - clause_offsets[k];
-            if (!pack_host(clauses3 + 3 * clause_offsets[k], n, stage.data() + (k - k0) * stride, f->max_var))
+            const int32_t* c3 = clauses3 + 3 * clause_offsets[k];
+            if (renumber) {
+                dense.resize(3 * n + 1);
+                if ((rc = map_in(f.get(), c3, 3 * n, dense.data()))) return rc;
+                c3 = dense.data();
+            }
+            if (!pack_host(c3, n, stage.data() + (k - k0) * stride, f->max_var))
                 return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
             f->entries.push_back(Entry{0, (uint32_t)k, (int32_t)n, -1, 0, 0});
         }
@@ -1049,7 +1111,11 @@ int ndp_frontier_from_host(const int32_t* clauses3, const size_t* clause_offsets
     for (auto& o : f->flat_off) o -= base;
     if (count) f->flat_choices.assign(choices + choice_offsets[0], choices + choice_offsets[count]);
     if (count == 0) f->flat_off.assign(1, 0);
-    for (int32_t l : f->flat_choices) f->max_var = std::max(f->max_var, std::abs(l));
+    if (renumber && (rc = map_in(f.get(), f->flat_choices.data(), f->flat_choices.size(), f->flat_choices.data()))) return rc;
+    for (int32_t l : f->flat_choices) {
+        if (l > kMaxVar || l < -kMaxVar) return fail(NDP_E_UNSUPPORTED, "choice magnitude exceeds 32766");
+        f->max_var = std::max(f->max_var, std::abs(l));
+    }
     *out = f.release();
     return NDP_OK;
 }
@@ -1067,8 +1133,17 @@ int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_
     // candidate root: everything below is undone if the frontier turns out not to descend from it
     std::vector<pclause> packed(std::max(n_clauses, (size_t)1));
     int max_var = f->max_var;
-    if (!pack_host(clauses3, n_clauses, packed.data(), max_var))
-        return fail(NDP_E_UNSUPPORTED, "literal magnitude exceeds 32766 (16-bit clause packing)");
+    std::vector<int32_t> dense;
+    const size_t ext_before = f->ext_of.size();
+    if (!f->ext_of.empty()) {                      // the frontier was renumbered when it was loaded: same map for its root
+        dense.resize(3 * n_clauses + 1);
+        if ((rc = map_in(f, clauses3, 3 * n_clauses, dense.data()))) return rc;
+        clauses3 = dense.data();
+    }
+    if (!pack_host(clauses3, n_clauses, packed.data(), max_var)) {
+        // (a root with ids beyond the codes under a frontier that needed no renumbering cannot be its ancestor)
+        return fail(f->ext_of.empty() ? NDP_E_INVALID : NDP_E_UNSUPPORTED, "root literal magnitude exceeds 32766 (16-bit clause packing)");
+    }
     const int old_max_var = f->max_var;
     f->root_c3.assign(clauses3, clauses3 + 3 * n_clauses);
     f->has_root = true;
@@ -1087,6 +1162,10 @@ int ndp_frontier_attach_root(ndp_frontier* f, const int32_t* clauses3, size_t n_
         f->has_root = false;
         f->states = false;
         f->max_var = old_max_var;
+        while (f->ext_of.size() > ext_before && ext_before > 0) {   // variables only the refused root named
+            f->dense_of.erase(f->ext_of.back());
+            f->ext_of.pop_back();
+        }
         return fail(code, msg);
     };
 #define ATT_TRY(expr)                                                                                       \
@@ -1825,19 +1904,39 @@ int batch_core(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, si
     std::vector<int> devs{f->device};
     for (int d = 0; d < have && (int)devs.size() < n_gpus; ++d)
         if (d != f->device) devs.push_back(d);
-    // peer-visible early-exit words: one per device, every kernel atomically lowers all of them
-    std::vector<unsigned long long*> best(n_gpus, nullptr);
+    // peer-visible early-exit words: one per device; a kernel atomically lowers the word of every device it
+    // can actually reach (peer access enabled), the others learn the winner from the host after the join
+    struct BestWords {
+        std::vector<unsigned long long*> p;
+        std::vector<int> dev;
+        ~BestWords() { for (size_t i = 0; i < p.size(); ++i) if (p[i]) { cudaSetDevice(dev[i]); cudaFree(p[i]); } }
+    } words;
+    words.p.assign(n_gpus, nullptr);
+    words.dev = devs;
+    std::vector<unsigned long long*>& best = words.p;
+    std::vector<std::vector<unsigned long long*>> reach(n_gpus);   // reach[i]: words device i may write (its own first)
+    std::vector<std::vector<char>> peer_ok(n_gpus, std::vector<char>(n_gpus, 0));
     const unsigned long long none = ~0ull;
     for (int i = 0; i < n_gpus; ++i) {
         CUDA_TRY(cudaSetDevice(devs[i]));
         for (int j = 0; j < n_gpus; ++j)
             if (i != j) {
                 int can = 0;
-                cudaDeviceCanAccessPeer(&can, devs[i], devs[j]);
-                if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0); if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); }
+                if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess) { cudaGetLastError(); can = 0; }
+                if (can) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                    if (e != cudaSuccess) { cudaGetLastError(); can = 0; }
+                }
+                peer_ok[i][j] = (char)can;
             }
         CUDA_TRY(cudaMalloc(&best[i], 8));
         CUDA_TRY(cudaMemcpy(best[i], &none, 8, cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < n_gpus; ++i) {
+        reach[i].push_back(best[i]);
+        for (int j = 0; j < n_gpus; ++j)
+            if (i != j && peer_ok[i][j]) reach[i].push_back(best[j]);
     }
     // build replicas serially (peer copies from the home device), then search concurrently
     const bool use_index = engine_uses_index(f);
@@ -1860,12 +1959,11 @@ int batch_core(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, si
     for (int i = 0; i < n_gpus; ++i)
         th.emplace_back([&, i]() {
             memset(&st[i], 0, sizeof(ndp_stats));
-            rcs[i] = dfs_on_device(f, devs[i], (size_t)i, (size_t)n_gpus, early_exit, best[i], best.data(), n_gpus,
-                                   none, verdict, &wins[i], &models[i], nodes, evals, &st[i]);
+            rcs[i] = dfs_on_device(f, devs[i], (size_t)i, (size_t)n_gpus, early_exit, best[i], reach[i].data(),
+                                   (int)reach[i].size(), none, verdict, &wins[i], &models[i], nodes, evals, &st[i]);
             if (rcs[i]) errs[i] = g_err;
         });
     for (auto& t : th) t.join();
-    for (int i = 0; i < n_gpus; ++i) { cudaSetDevice(devs[i]); cudaFree(best[i]); }
     cudaSetDevice(f->device);
     for (int i = 0; i < n_gpus; ++i)
         if (rcs[i]) return fail(rcs[i], errs[i]);
@@ -2079,6 +2177,7 @@ int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, 
         if (model_len) *model_len = m.size();
         if (model) {
             if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            map_out(f, m.data(), m.size());
             memcpy(model, m.data(), m.size() * sizeof(int32_t));
         }
     }
@@ -2180,6 +2279,7 @@ int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early
         if (model_len) *model_len = m.size();
         if (model && !m.empty()) {
             if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            map_out(f, m.data(), m.size());
             memcpy(model, m.data(), m.size() * sizeof(int32_t));
         }
     }
@@ -2328,6 +2428,7 @@ int ndp_dfs_pieces_fold(ndp_piece_run* run, const uint32_t* first_model, uint8_t
         if (model_len) *model_len = m.size();
         if (model) {
             if (m.size() > model_cap) return fail(NDP_E_INVALID, "model buffer too small");
+            map_out(run->f, m.data(), m.size());
             memcpy(model, m.data(), m.size() * sizeof(int32_t));
         }
     }
@@ -2370,11 +2471,20 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
             const double t_split = now_ms();
             if ((rc = run_split(f->device, *ix, *rep, target, split, stats))) return rc;
             if (stats) stats->kernel_ms += now_ms() - t_split;   // run_split returns after the kernel (it reads its state back)
-            if (split.active) return batch_over_pieces(f, *ix, split, n_gpus, early_exit, verdict, winner, model, model_cap,
-                                                       model_len, stats);
+            if (split.active) {
+                size_t len = 0;
+                rc = batch_over_pieces(f, *ix, split, n_gpus, early_exit, verdict, winner, model, model_cap, &len, stats);
+                if (!rc && model) map_out(f, model, len);
+                if (model_len) *model_len = len;
+                return rc;
+            }
         }
     }
-    return batch_core(f, n_gpus, early_exit, verdict, winner, model, model_cap, model_len, nullptr, nullptr, stats);
+    size_t len = 0;
+    rc = batch_core(f, n_gpus, early_exit, verdict, winner, model, model_cap, &len, nullptr, nullptr, stats);
+    if (!rc && model) map_out(f, model, len);
+    if (model_len) *model_len = len;
+    return rc;
 }
 
 }  // extern "C"

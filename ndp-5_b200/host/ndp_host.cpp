@@ -269,9 +269,15 @@ struct Out {   // buffered text sink
     FILE* f;
     std::string buf;
     explicit Out(FILE* f_) : f(f_) { buf.reserve(1 << 20); }
+    bool failed = false;   // latched: a short write anywhere in the stream (ENOSPC, quota) fails the whole save
     void put(const char* s) { buf += s; if (buf.size() > (1u << 20) - 256) flush(); }
     void put_int(int v) { char b[16]; auto r = std::to_chars(b, b + sizeof b, v); buf.append(b, r.ptr); if (buf.size() > (1u << 20) - 256) flush(); }
-    bool flush() { size_t n = fwrite(buf.data(), 1, buf.size(), f); bool ok = n == buf.size(); buf.clear(); return ok; }
+    bool flush() {
+        size_t n = fwrite(buf.data(), 1, buf.size(), f);
+        if (n != buf.size() || ferror(f)) failed = true;
+        buf.clear();
+        return !failed;
+    }
 };
 std::string json_double(double v) {   // shortest round-trip form, always with a fraction or exponent
     char b[64];
@@ -407,7 +413,7 @@ struct In {   // buffered character source with one-character look-ahead
     }
     bool integer(int32_t& out) {
         double v; bool i; long long iv;
-        if (!number(v, i, iv) || iv > INT_MAX || iv < INT_MIN) return false;
+        if (!number(v, i, iv) || (!i && v != (double)iv) || iv > INT_MAX || iv < INT_MIN) return false;   // 2.0 is 2; 1.5 is not a literal
         out = (int32_t)iv;
         return true;
     }

@@ -91,14 +91,57 @@ def test_bfs_edge_cases(nd, oracle):
             fr.free()
 
 
-def test_unsupported_literal_width_fails_loudly(nd):
-    for bad in (40000, 32767, -32767):
-        with pytest.raises(nd.NdpError) as ei:
-            nd.bfs(np.array([[1, 2, bad]], dtype=np.int32), 1, False, -1)
-        assert ei.value.code == nd.NDP_E_UNSUPPORTED
-        with pytest.raises(nd.NdpError) as ei:
-            nd.frontier_from_host([(np.array([[1, 2, bad]], dtype=np.int32), np.zeros(0, np.int32))])
-        assert ei.value.code == nd.NDP_E_UNSUPPORTED
+def test_sparse_variable_ids_up_to_2_pow_30(nd, oracle, cnf_text):
+    """The reference's Clause3 is `int l[3]` (ClauseSetPool.hpp:37-39): any variable id is legal.  The kernels pack
+    literals in 16-bit codes, so the library renumbers at the ABI when the ids do not fit (only variables that occur
+    need a code) and maps every literal back on the way out: frontier clauses, choices and models carry the
+    caller's ids.  Parity against the oracle on the caller's CNF, BFS + DFS + resume with root."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for trial in range(12):
+        nv = int(rng.integers(3, 40))
+        A = util_cnf.random_cnf(rng, nv, int(rng.integers(5, 150)), p_unit=0.03, p_binary=0.12, p_dup=0.04, p_taut=0.04)
+        cases.append(A)
+    cases.append(oracle.parse(cnf_text("rsaFACT-12bit")))
+    cases.append(oracle.parse(cnf_text("prime-12bit")))
+    for trial, A in enumerate(cases):
+        ids = np.unique(np.abs(A[A != 0]))
+        big = rng.choice(np.arange(40000, 1 << 30, 1 << 12), size=len(ids), replace=False) + rng.integers(0, 1 << 12, len(ids))
+        if trial % 3 == 0:
+            big[0] = (1 << 30)                                  # the largest id the test names
+        if trial % 3 == 1:
+            big[: len(big) // 2] = ids[: len(big) // 2]         # a mix of small and huge ids
+        lut = dict(zip(ids.tolist(), big.tolist()))
+        B = np.vectorize(lambda l: 0 if l == 0 else (lut[abs(l)] if l > 0 else -lut[abs(l)]))(A).astype(np.int32)
+        for D, ovr, Q in [(0, True, int(rng.integers(2, 12))), (int(rng.integers(1, 60)), False, -1)]:
+            fr, o = check_bfs_against_oracle(nd, oracle, B, D, ovr, Q, ("sparse", trial, D, Q))
+            r = check_dfs_against_oracle(nd, oracle, fr, o["frontier"], ("sparse", trial, D, Q))
+            if r["winner"] is not None:
+                assert util_cnf.satisfies(B, r["model"])
+            if len(fr):
+                fr2 = nd.frontier_from_host(o["frontier"])       # resume path with the caller's ids, then its root
+                assert fr2.attach_root(B) is True
+                r2 = fr2.dfs_shard()
+                assert r2["verdict"].tolist() == r["verdict"].tolist() and r2["nodes"].tolist() == r["nodes"].tolist()
+                assert r2["winner"] == r["winner"] and r2["model"].tolist() == r["model"].tolist()
+                c2, h2 = fr2.get(len(fr) - 1)
+                assert (c2 == o["frontier"][-1][0]).all() and (h2 == o["frontier"][-1][1]).all()
+                fr2.free()
+            fr.free()
+
+
+def test_too_many_distinct_variables_fails_loudly(nd):
+    """What remains unsupported is a resource limit, not an id range: more than 32766 DISTINCT variables."""
+    v = np.arange(1, 3 * 11000 + 1, dtype=np.int32).reshape(-1, 3) + 100000
+    with pytest.raises(nd.NdpError) as ei:
+        nd.bfs(v, 1, False, -1)
+    assert ei.value.code == nd.NDP_E_UNSUPPORTED
+    with pytest.raises(nd.NdpError) as ei:
+        nd.frontier_from_host([(v, np.zeros(0, np.int32))])
+    assert ei.value.code == nd.NDP_E_UNSUPPORTED
+    with pytest.raises(nd.NdpError) as ei:
+        nd.bfs(np.array([[1, 2, -2147483648]], dtype=np.int32), 1, False, -1)
+    assert ei.value.code == nd.NDP_E_UNSUPPORTED
 
 
 # ------------------------------------------------------------------------------------------ DFS

@@ -240,3 +240,24 @@ def test_bfs_json_cross_reads_with_reference(host, ref, oracle, tmp_path, cnf_te
         assert t == 1.5 and len(back) == len(items)
         assert all((a == c).all() and (b == d).all() for (a, b), (c, d) in zip(items, back))
         ref.frontier_free(h)
+
+
+def test_bfs_json_reader_rejects_fractional_literals(host, tmp_path):
+    """A literal is an integer: 2.0 reads as 2 (what nlohmann's get<int>() gives), 1.5 is refused (round-1 advisor)."""
+    ok = str(tmp_path / "ok.json")
+    open(ok, "w").write('{"bfs_results": [{"choices": [2.0, -3], "clauses": [[1, 2.0, -3e0]]}], "bfs_time": 0.5}')
+    back, t = host.read_bfs_json(ok)
+    assert t == 0.5 and back[0][1].tolist() == [2, -3] and back[0][0].tolist() == [[1, 2, -3]]
+    for bad in ('{"bfs_results": [{"choices": [1.5], "clauses": []}], "bfs_time": 0.5}',
+                '{"bfs_results": [{"choices": [], "clauses": [[1, 2, 2.25]]}], "bfs_time": 0.5}'):
+        p = str(tmp_path / "bad.json")
+        open(p, "w").write(bad)
+        assert host.read_bfs_json(p) is None
+
+
+def test_bfs_json_writer_reports_a_full_disk(host, tmp_path):
+    """A short write in mid-stream must fail the save (round-1 advisor): /dev/full accepts the open and fails every flush."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    items = [(np.arange(1, 3001, dtype=np.int32).reshape(-1, 3), np.arange(1, 50, dtype=np.int32))] * 300   # > one 1 MB buffer
+    assert host.write_bfs_json("/dev/full", items, 1.0) != 0
