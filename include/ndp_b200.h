@@ -205,6 +205,12 @@ int ndp_dfs_pieces_fold(ndp_piece_run* run, const uint32_t* first_model, uint8_t
                         ndp_stats* stats);
 void ndp_dfs_pieces_end(ndp_piece_run* run);
 
+/* Progress of the DFS call(s) in flight in this process, for the reference's 1 Hz status line
+ * "DFS time: .. seconds  -  Remaining Queue Size: ..  -  Active Workers: .." (NDP:1271-1288).  May be called
+ * from any host thread while another one is inside ndp_dfs_*: units (subproblems, or the pieces they were
+ * cut into) handed to warps so far / in total, summed over the devices that are searching right now. */
+int ndp_dfs_progress(size_t* units_pulled, size_t* units_total, int* devices_active);
+
 /* Whole frontier on n_gpus devices of this process (static interleaved split k -> k mod n_gpus,
  * one host thread per device, peer-visible early-exit flag).  n_gpus <= 0 means 1.  A frontier too
  * narrow for the devices (-d 12, -d 20: ONE subproblem) is first cut into DFS-order pieces on its home

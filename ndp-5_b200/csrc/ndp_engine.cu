@@ -11,6 +11,7 @@
 #include "ndp_split.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -80,6 +81,35 @@ void* pinned_scratch(int slot, size_t bytes) {
     if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped) != cudaSuccess) return nullptr;
     items.push_back(Item{dev, slot, bytes, p});
     return p;
+}
+
+// Progress of the DFS calls in flight, one record per device: what the reference's 1 Hz status line shows
+// (NDP:1271-1288: remaining queue size, active workers).  `pulled` is a mapped pinned word the DFS kernel
+// stores the last unit index into (one posted write per unit); any host thread may read it.
+struct ProgressSlot { volatile unsigned* pulled = nullptr; unsigned* d_pulled = nullptr; std::atomic<unsigned long long> total{0}; std::atomic<int> active{0}; };
+ProgressSlot g_progress[16];
+std::mutex g_progress_mtx;
+int progress_arm(int device, size_t total, unsigned** d_word) {
+    *d_word = nullptr;
+    if (device < 0 || device >= 16) return NDP_OK;
+    ProgressSlot& ps = g_progress[device];
+    {
+        std::lock_guard<std::mutex> lock(g_progress_mtx);
+        if (!ps.pulled) {
+            void* h = nullptr;
+            if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return NDP_OK; }
+            ps.pulled = static_cast<volatile unsigned*>(h);
+            if (cudaHostGetDevicePointer((void**)&ps.d_pulled, h, 0) != cudaSuccess) { cudaGetLastError(); ps.d_pulled = nullptr; }
+        }
+    }
+    *ps.pulled = 0u;
+    ps.total.store(total);
+    ps.active.store(1);
+    *d_word = ps.d_pulled;
+    return NDP_OK;
+}
+void progress_disarm(int device) {
+    if (device >= 0 && device < 16) g_progress[device].active.store(0);
 }
 
 int requested_engine() {
@@ -1703,6 +1733,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.best_piece = b_bestp.as<unsigned int>();
         p.first = first; p.stride = stride; p.n_local = nl;
         p.next = b_next.as<unsigned int>();
+        progress_arm(device, nl, &p.progress);
         p.best = d_best;
         p.n_peers = 0;
         for (int d = 0; d < n_peers && d < 8; ++d)
@@ -1755,7 +1786,11 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1, 0));
     t_launched = now_ms();
-    CUDA_TRY(cudaEventSynchronize(ev1));
+    {
+        cudaError_t se = cudaEventSynchronize(ev1);
+        progress_disarm(device);
+        CUDA_TRY(se);
+    }
     t_kernel_done = now_ms();
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
@@ -2440,6 +2475,24 @@ void ndp_dfs_pieces_end(ndp_piece_run* run) {
     cudaSetDevice(run->f->device);
     run->ps.release();
     delete run;
+}
+
+int ndp_dfs_progress(size_t* units_pulled, size_t* units_total, int* devices_active) {
+    unsigned long long pulled = 0, total = 0;
+    int active = 0;
+    for (ProgressSlot& ps : g_progress) {
+        if (!ps.active.load() || !ps.pulled) continue;
+        const unsigned long long t = ps.total.load();
+        unsigned long long q = (unsigned long long)*ps.pulled + 1ull;   // the word holds the LAST index handed out
+        if (*ps.pulled == 0u && t == 0) q = 0;
+        pulled += std::min(q, t);
+        total += t;
+        ++active;
+    }
+    if (units_pulled) *units_pulled = (size_t)pulled;
+    if (units_total) *units_total = (size_t)total;
+    if (devices_active) *devices_active = active;
+    return NDP_OK;
 }
 
 int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict, size_t* winner,

@@ -901,6 +901,7 @@ struct IndexParams {
     int pend_words, trail_cap;
     unsigned long long first, stride, n_local;   // n_local = pieces
     unsigned int* next;
+    unsigned int* progress;           // host-mapped word: last unit pulled (ndp_dfs_progress), or nullptr
     unsigned long long* best;
     unsigned long long* peer_best[8];
     int n_peers;
@@ -934,7 +935,10 @@ __global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant
 
     for (;;) {
         unsigned q = 0;
-        if (lane == 0) q = atomicAdd(p.next, 1u);
+        if (lane == 0) {
+            q = atomicAdd(p.next, 1u);
+            if (p.progress) *(volatile unsigned*)p.progress = q;   // posted write to pinned host memory, once per unit
+        }
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= p.n_local) break;
         const unsigned o = p.orig ? (unsigned)p.orig[q] : q;

@@ -15,7 +15,9 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <unistd.h>
@@ -179,9 +181,25 @@ int main(int argc, char** argv) {
     std::vector<int32_t> model((size_t)h.num_vars + clauses.size() + 16);
     size_t winner = SIZE_MAX, model_len = 0;
     ndp_stats st;
-    if (ndp_dfs_batch(frontier, n_gpus, cli.exhaustive ? 0 : 1, verdict.data(), &winner, model.data(), model.size(),
-                      &model_len, &st) != NDP_OK)
-        return die("DFS");
+    // the reference's 1 Hz status line (NDP:1271-1288), fed by the kernels' progress word
+    std::atomic<bool> dfs_done(false);
+    std::thread time_printer([&]() {
+        for (;;) {
+            for (int i = 0; i < 10 && !dfs_done.load(); ++i) usleep(100000);
+            if (dfs_done.load()) break;
+            const long elapsed = (long)std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - dfs_start).count();
+            size_t pulled = 0, total = 0;
+            int active = 0;
+            ndp_dfs_progress(&pulled, &total, &active);
+            std::cout << "\033[2K\r    DFS time: " << elapsed << " seconds  -  Remaining Queue Size: " << (total - pulled)
+                      << "  -  Active Workers: " << active << std::flush;
+        }
+    });
+    const int dfs_rc = ndp_dfs_batch(frontier, n_gpus, cli.exhaustive ? 0 : 1, verdict.data(), &winner, model.data(),
+                                     model.size(), &model_len, &st);
+    dfs_done.store(true);
+    time_printer.join();
+    if (dfs_rc != NDP_OK) return die("DFS");
     const double dfs_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - dfs_start).count();
 
     Report r;

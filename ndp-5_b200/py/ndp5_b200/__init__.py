@@ -81,6 +81,7 @@ def _load():
         "ndp_dfs_pieces_fold": (C.c_int, [C.c_void_p, _u32p, _u8p, _u64p, _u64p, _szp, _i32p, C.c_size_t, _szp,
                                           C.POINTER(Stats)]),
         "ndp_dfs_pieces_end": (None, [C.c_void_p]),
+        "ndp_dfs_progress": (C.c_int, [_szp, _szp, C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -114,6 +115,13 @@ def set_split(pieces):
     """-1 automatic, 0 never split a shard into pieces, > 0 piece target (ndp_set_split)."""
     pieces = {"auto": -1, "off": 0}.get(pieces, pieces)
     _check(lib.ndp_set_split(int(pieces)))
+
+
+def dfs_progress():
+    """(units pulled, units in total, devices searching) of the DFS call(s) in flight -- callable from another thread."""
+    a, b, c = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+    _check(lib.ndp_dfs_progress(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def device_count():

@@ -9,7 +9,9 @@ every 2-input gate is 4 ternary truth-table clauses; product bits are unit claus
     python tools/gen_cnf.py N BITS out.dimacs      # BITS = total product bits (even)
 
 Named corpus (fixed semiprimes / primes from SURVEY.md §8c):
-    python tools/gen_cnf.py --named rsaFACT-32bit out.dimacs
+    python tools/gen_cnf.py --named rsaFACT-32bit out.dimacs [minimal|purdom-sabry]
+Input check (what the reference requires of ANY generator's file, README.md:18-26):
+    python tools/gen_cnf.py --check some.dimacs
 """
 import sys
 
@@ -98,22 +100,80 @@ def multiplier_cnf(N, bits):
     return nvars, clauses, A, B
 
 
-def dimacs_text(N, bits):
+def dimacs_text(N, bits, header="minimal"):
+    """header="minimal": the four lines the reference's regexes need (NDP-5_6_7.cpp:1591-1592,1598, 948-949).
+    header="purdom-sabry": the fuller comment block of the generators the reference's README names
+    (README.md:18-26: Purdom & Sabry's CNF generator, GridSAT/CNF_FACT-MULT) -- a provenance line, the product line,
+    an output-variables line, the two input lines, blank comment lines.  Neither generator is available offline, so the
+    block is reconstructed from the reference's own regexes and README; what is CHECKED (tests/test_gen_cnf.py) is that
+    the reference's parser and header scrape read both variants identically."""
     nvars, clauses, A, B = multiplier_cnf(N, bits)
-    lines = [
-        "c Circuit for product = %d [%s]" % (N, bin(N)[2:]),
-        "c Variables for first input [msb,...,lsb]: [%s]" % ", ".join(map(str, A[::-1])),
-        "c Variables for second input [msb,...,lsb]: [%s]" % ", ".join(map(str, B[::-1])),
-        "p cnf %d %d" % (nvars, len(clauses)),
-    ]
+    product = "c Circuit for product = %d [%s]" % (N, bin(N)[2:])
+    first = "c Variables for first input [msb,...,lsb]: [%s]" % ", ".join(map(str, A[::-1]))
+    second = "c Variables for second input [msb,...,lsb]: [%s]" % ", ".join(map(str, B[::-1]))
+    problem = "p cnf %d %d" % (nvars, len(clauses))
+    if header == "minimal":
+        lines = [product, first, second, problem]
+    elif header == "purdom-sabry":
+        outs = [abs(c[0]) for c in clauses[-bits:]] if bits <= len(clauses) else []
+        lines = ["c Problem generated from an array multiplication circuit (tools/gen_cnf.py, Purdom-Sabry style header)",
+                 "c", product, "c Variables for output [msb,...,lsb]: [%s]" % ", ".join(map(str, outs[::-1])), first, second,
+                 "c", "c", problem]
+    else:
+        raise ValueError("unknown header style %r" % header)
     lines += [" ".join(map(str, c)) + " 0" for c in clauses]
     return "\n".join(lines) + "\n"
 
 
-def write_named(name, path):
+def check_text(text):
+    """What the reference REQUIRES of an input file, checked the way it reads one (NDP-5_6_7.cpp:619-642 parser,
+    1590-1615 / 946-990 header scrape).  Returns a list of problem strings (empty = the file is usable):
+    missing header regexes, clause lines whose width is not 1 or 3 (the reference silently drops them, NDP:639),
+    several clauses on one line, literals beyond the declared variable count."""
+    import re
+    problems = []
+    m = re.search(r"p cnf ([0-9]+) ([0-9]+)", text)
+    if not m:
+        problems.append("no `p cnf V C` line (NDP:1592)")
+    if not re.search(r"Circuit for product = ([0-9]+) \[", text):
+        problems.append("no `Circuit for product = N [` line (NDP:1591)")
+    if not re.search(r"Variables for first input \[msb,...,lsb\]: \[(.*?)\]", text):
+        problems.append("no `Variables for first input [msb,...,lsb]: [...]` line (NDP:948)")
+    if not re.search(r"Variables for second input \[msb,...,lsb\]: \[.*?,\s*(\d+)\]", text):
+        problems.append("no `Variables for second input [msb,...,lsb]: [..., v]` line (NDP:949,1598)")
+    nvars = int(m.group(1)) if m else None
+    n_declared = int(m.group(2)) if m else None
+    n_ok = 0
+    for ln, line in enumerate(text.splitlines(), 1):
+        t = line.strip()
+        if not t or t[0] in "cp%":
+            continue
+        toks = t.split()
+        try:
+            lits = [int(x) for x in toks]
+        except ValueError:
+            problems.append("line %d: not a clause: %r" % (ln, t[:40]))
+            continue
+        if lits.count(0) > 1 or (lits and lits[-1] != 0):
+            problems.append("line %d: the reference reads ONE clause per line, terminated by 0" % ln)
+            continue
+        body = lits[:-1]
+        if len(body) not in (1, 3):
+            problems.append("line %d: clause of width %d is silently DROPPED by the reference (NDP:639); only 1 and 3 are read"
+                            % (ln, len(body)))
+            continue
+        if nvars is not None and any(abs(l) > nvars for l in body):
+            problems.append("line %d: literal beyond the declared %d variables" % (ln, nvars))
+        n_ok += 1
+    if n_declared is not None and n_ok != n_declared:
+        problems.append("`p cnf` declares %d clauses, %d usable clause lines found" % (n_declared, n_ok))
+    return problems
+
+
+def write_named(name, path, header="minimal"):
     N, bits = NAMED[name]
     with open(path, "w") as f:
-        f.write(dimacs_text(N, bits))
+        f.write(dimacs_text(N, bits, header))
     return N, bits
 
 
@@ -121,6 +181,16 @@ def main(argv):
     if len(argv) == 4 and argv[1] == "--named":
         print(write_named(argv[2], argv[3]))
         return 0
+    if len(argv) == 5 and argv[1] == "--named" and argv[4] in ("minimal", "purdom-sabry"):
+        print(write_named(argv[2], argv[3], argv[4]))
+        return 0
+    if len(argv) == 3 and argv[1] == "--check":
+        with open(argv[2], errors="replace") as f:
+            problems = check_text(f.read())
+        for p in problems:
+            print(p)
+        print("%s: %s" % (argv[2], "usable by NDP as it is" if not problems else "%d problem(s)" % len(problems)))
+        return 1 if problems else 0
     if len(argv) != 4:
         sys.stderr.write(__doc__)
         return 2
