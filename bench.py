@@ -405,9 +405,19 @@ def run_b200(args, workload):
         sampler.start()
         time.sleep(0.3)
 
-    for _ in range(args.warmup):
-        flush.zero_()
-        out = step(A, (D, ovr, Q))
+    warm_note = "%d untimed steps of the same workload" % args.warmup
+    if args.warmup_legacy:
+        # a step of minutes (64-bit exhaustive): warm the device, the pools and the code paths on the small legacy
+        # workload instead of repeating the long step three times
+        Aw = clause_array(parse_workload(LEGACY_WORKLOAD)[0])[0]
+        for _ in range(args.warmup):
+            flush.zero_()
+            step(Aw, parse_workload(LEGACY_WORKLOAD)[3])
+        warm_note = "%d untimed steps of %s (a step of this workload takes minutes)" % (args.warmup, LEGACY_WORKLOAD)
+    else:
+        for _ in range(args.warmup):
+            flush.zero_()
+            out = step(A, (D, ovr, Q))
     barrier()
     t0 = time.time()
     step_s, dev_ms, launches = [], [], 0
@@ -584,6 +594,7 @@ def run_b200(args, workload):
                        "timed_region": "BFS level loop + DFS cut + DFS kernel, device time (CUDA events on the launching "
                                        "stream, inside the library), mean over steps, max over ranks",
                        "l2": "256 MB flush write before every step; the DFS reads > 126 MB of piece state slots per step",
+                       "warmup": warm_note,
                        "parity": "BFS counters, n_sat, first_sat and (golden_checked) per-subproblem verdict / node / "
                                  "clause-eval counts asserted against reference-produced fixtures on every run"},
             "e2e": e2e, "gpu_launches": int(launches),
@@ -635,6 +646,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
+    ap.add_argument("--warmup-legacy", action="store_true",
+                    help="run the warm-up steps on the small legacy workload (for workloads whose step takes minutes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.steps = max(args.steps, 1)

@@ -8,6 +8,7 @@
 #include "../../include/ndp_b200.h"
 #include "ndp_kernels.cuh"
 #include "ndp_index.cuh"
+#include "ndp_index_group.cuh"
 #include "ndp_split.cuh"
 
 #include <algorithm>
@@ -1374,7 +1375,9 @@ bool engine_uses_index(const ndp_frontier* f) {
 
 struct IndexLaunchPlan {
     int warps_per_cta, ctas_per_sm, grid, smem_bytes;
+    int groups;          // searches per warp (ndp_index_group.cuh): 1, 2 (16-lane groups) or 4 (8-lane groups)
     IndexParams p;
+    int searchers() const { return grid * warps_per_cta * groups; }   // pieces in flight on the device
 };
 
 int plan_index(int device, const IndexRoot& ix, int max_var, IndexLaunchPlan& plan) {
@@ -1392,19 +1395,39 @@ int plan_index(int device, const IndexRoot& ix, int max_var, IndexLaunchPlan& pl
     if ((size_t)p.warp_bytes > (size_t)smem_optin)
         return fail(NDP_E_UNSUPPORTED, "clause count too large for the shared-memory bitmaps");
     const int sm_smem = 233472;
+    // Searches per warp.  The kernel is bound by instruction issue and almost all of a node's instructions are
+    // lane-independent, so several pieces per warp (lane groups walking the unit step in lockstep) multiply the
+    // node rate -- as long as shared memory still holds enough pieces to keep a few warps per scheduler resident.
+    // Groups need the plain root (B[2] summary, no {0,0,0} clause, no repeated variable in a clause).
+    // Measured (profiles/r2_dfs_group_*): 32-bit CNF (2.1 KB slots, 104 pieces per SM) 1.53 -> 1.06 ms with 4 groups,
+    // half the warp instructions per node; 48-bit (4.3 KB slots) no gain with 2 groups and a loss with 4 -- there the
+    // kernel is bound by resident pieces / per-node latency, and the larger carve-out takes the index's L1 away.
+    const int pieces_per_sm = (int)((size_t)sm_smem / ((size_t)p.warp_bytes + 256));
+    int groups = ix.plain && pieces_per_sm >= 96 ? 4 : 1;
+    if (const char* s = getenv("NDP_DFS_GROUPS")) {
+        const int g = atoi(s);
+        if (ix.plain && (g == 1 || g == 2 || g == 4)) groups = g;
+    }
     int best_total = 0, best_w = 1, best_ctas = 1;
     int cap_warps = 32;   // resident warps per SM; tunable for experiments
     if (const char* s = getenv("NDP_INDEX_WARPS_PER_SM")) cap_warps = std::max(1, std::min(64, atoi(s)));
-    for (int w : {4, 2, 1}) {
-        size_t cta = (size_t)p.warp_bytes * w;
-        if (cta > (size_t)smem_optin) continue;
-        int ctas = (int)std::min<size_t>(cap_warps / w, (size_t)sm_smem / (cta + 1024));
-        if (ctas < 1) continue;
-        if (w * ctas > best_total) { best_total = w * ctas; best_w = w; best_ctas = ctas; }
+    for (;;) {
+        best_total = 0;
+        for (int w : {4, 2, 1}) {
+            size_t cta = (size_t)p.warp_bytes * w * groups;
+            if (cta > (size_t)smem_optin) continue;
+            int ctas = (int)std::min<size_t>(cap_warps / w, (size_t)sm_smem / (cta + 1024));
+            if (ctas < 1) continue;
+            if (w * ctas > best_total) { best_total = w * ctas; best_w = w; best_ctas = ctas; }
+        }
+        if (best_total > 0 || groups == 1) break;
+        groups /= 2;      // the slots of `groups` searches do not fit one CTA: fewer searches per warp
     }
+    if (best_total == 0) return fail(NDP_E_UNSUPPORTED, "clause count too large for the shared-memory bitmaps");
+    plan.groups = groups;
     plan.warps_per_cta = best_w;
     plan.ctas_per_sm = best_ctas;
-    plan.smem_bytes = p.warp_bytes * best_w;
+    plan.smem_bytes = p.warp_bytes * best_w * groups;
     plan.grid = sms * best_ctas;
     return NDP_OK;
 }
@@ -1658,7 +1681,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     int n_warps, model_stride;
     if (use_index) {
         if ((rc = plan_index(device, *ix, f->max_var, iplan))) return rc;
-        n_warps = iplan.grid * iplan.warps_per_cta;
+        n_warps = iplan.searchers();    // searches in flight: every per-"warp" array below is per searcher
         model_stride = iplan.p.trail_cap;
     } else {
         if ((rc = plan_dfs(device, rep->n_max, f->max_var, plan))) return rc;
@@ -1684,6 +1707,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     DevBuf b_verdict, b_nodes, b_evals, b_reb, b_next, b_best, b_bestp, b_msub, b_mlen, b_models, b_scratch, b_snaps;
     int snap_depth = 4;
     if (const char* e = getenv("NDP_DFS_SNAPS")) snap_depth = std::max(0, std::min(32, atoi(e)));
+    if (use_index && iplan.groups > 1) snap_depth = std::min(snap_depth, 32 / iplan.groups);   // lane k of a group holds |A| of snapshot k
     const size_t nl1 = std::max(nl, (size_t)1);
     CUDA_TRY(dev_alloc(&b_verdict.p, nl1));
     CUDA_TRY(dev_alloc(&b_nodes.p, nl1 * 8));
@@ -1751,7 +1775,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.models = b_models.as<int32_t>();
         // the common case (B[2] summary, no {0,0,0} clause, no variable twice in a clause) runs the kernel
         // with those tests compiled out
-        auto kern = ix->plain ? dfs_index_kernel<true> : dfs_index_kernel<false>;
+        auto kern = iplan.groups == 4 ? dfs_index_group_kernel<8> : iplan.groups == 2 ? dfs_index_group_kernel<16>
+                    : ix->plain ? dfs_index_kernel<true> : dfs_index_kernel<false>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
         {
             // leave L1 everything the resident CTAs do not need: the root index is read through it
@@ -2363,7 +2388,7 @@ int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_e
         // static deal piece -> rank to balance statistically (>= 4096 per rank), and only where cutting pays
         // (split_target's test: shard starved or subproblems still deep).  Each rank then refines its own
         // share down to pieces-per-warp granularity inside dfs_on_device -- in parallel, on its own data.
-        const size_t n_warps = (size_t)iplan.grid * iplan.warps_per_cta * world;
+        const size_t n_warps = (size_t)iplan.searchers() * world;
         size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive);
         if (g_split < 0 && !getenv("NDP_SPLIT")) {            // automatic policy
             const size_t coarse = (size_t)4096 * world;
@@ -2512,7 +2537,7 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         CUDA_TRY(cudaSetDevice(f->device));
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
-        const int n_warps = iplan.grid * iplan.warps_per_cta;
+        const int n_warps = iplan.searchers();
         double alive = 0;
         for (const Entry& e : f->entries) alive += (double)e.n;
         alive /= (double)f->entries.size();
