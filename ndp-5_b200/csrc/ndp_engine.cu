@@ -1376,6 +1376,7 @@ bool engine_uses_index(const ndp_frontier* f) {
 struct IndexLaunchPlan {
     int warps_per_cta, ctas_per_sm, grid, smem_bytes;
     int groups;          // searches per warp (ndp_index_group.cuh): 1, 2 (16-lane groups) or 4 (8-lane groups)
+    bool global_state;   // state slots in global memory (experiment knob NDP_DFS_GLOBAL_STATE, groups > 1 only)
     IndexParams p;
     int searchers() const { return grid * warps_per_cta * groups; }   // pieces in flight on the device
 };
@@ -1404,13 +1405,30 @@ int plan_index(int device, const IndexRoot& ix, int max_var, IndexLaunchPlan& pl
     // kernel is bound by resident pieces / per-node latency, and the larger carve-out takes the index's L1 away.
     const int pieces_per_sm = (int)((size_t)sm_smem / ((size_t)p.warp_bytes + 256));
     int groups = ix.plain && pieces_per_sm >= 96 ? 4 : 1;
+    // Larger slots: what bounds the kernel is pieces in flight / per-node latency, and shared memory holds too few
+    // pieces (48-bit: 51 per SM, 64-bit: 29).  There the slots live in GLOBAL memory (L1/L2-served) under the lane-group
+    // kernel: 48 warps x 4 groups = 192 pieces per SM.  48-bit exhaustive 600 -> 453 ms, 64-bit to the factors 50.4 -> 35.3 s
+    // (32 warps) on one B200.
+    bool global_state = ix.plain && pieces_per_sm < 96;
+    if (const char* s = getenv("NDP_DFS_GLOBAL_STATE")) global_state = ix.plain && atoi(s) != 0;
+    if (global_state) groups = 4;
     if (const char* s = getenv("NDP_DFS_GROUPS")) {
         const int g = atoi(s);
         if (ix.plain && (g == 1 || g == 2 || g == 4)) groups = g;
     }
+    plan.global_state = groups > 1 && global_state;
+    if (plan.global_state) {
+        plan.groups = groups;
+        plan.warps_per_cta = 4;
+        plan.ctas_per_sm = 12;
+        if (const char* s = getenv("NDP_INDEX_WARPS_PER_SM")) plan.ctas_per_sm = std::max(1, std::min(12, atoi(s) / 4));
+        plan.smem_bytes = 0;
+        plan.grid = sms * plan.ctas_per_sm;
+        return NDP_OK;
+    }
     int best_total = 0, best_w = 1, best_ctas = 1;
-    int cap_warps = 32;   // resident warps per SM; tunable for experiments
-    if (const char* s = getenv("NDP_INDEX_WARPS_PER_SM")) cap_warps = std::max(1, std::min(64, atoi(s)));
+    int cap_warps = 48;   // resident warps per SM (above 32 the 40-register build of the kernel runs): 48-bit CNF 638 -> 600 ms
+    if (const char* s = getenv("NDP_INDEX_WARPS_PER_SM")) cap_warps = std::max(1, std::min(48, atoi(s)));
     for (;;) {
         best_total = 0;
         for (int w : {4, 2, 1}) {
@@ -1775,8 +1793,18 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         p.models = b_models.as<int32_t>();
         // the common case (B[2] summary, no {0,0,0} clause, no variable twice in a clause) runs the kernel
         // with those tests compiled out
-        auto kern = iplan.groups == 4 ? dfs_index_group_kernel<8> : iplan.groups == 2 ? dfs_index_group_kernel<16>
-                    : ix->plain ? dfs_index_kernel<true> : dfs_index_kernel<false>;
+        const bool dense = iplan.warps_per_cta * iplan.ctas_per_sm > 32;   // more than 32 warps per SM: the 40-register build
+        DevBuf b_gstate;
+        p.gstate = nullptr;
+        if (iplan.global_state) {
+            CUDA_TRY(dev_alloc(&b_gstate.p, (size_t)n_warps * p.warp_bytes));
+            p.gstate = b_gstate.as<unsigned char>();
+        }
+        auto kern = iplan.global_state ? (iplan.groups == 4 ? (dense ? dfs_index_group_kernel<8, true, 12> : dfs_index_group_kernel<8, true>)
+                                                            : (dense ? dfs_index_group_kernel<16, true, 12> : dfs_index_group_kernel<16, true>))
+                    : iplan.groups == 4 ? dfs_index_group_kernel<8> : iplan.groups == 2 ? dfs_index_group_kernel<16>
+                    : ix->plain ? (dense ? dfs_index_kernel<true, 12> : dfs_index_kernel<true, 8>)
+                                : (dense ? dfs_index_kernel<false, 12> : dfs_index_kernel<false, 8>);
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, iplan.smem_bytes));
         {
             // leave L1 everything the resident CTAs do not need: the root index is read through it

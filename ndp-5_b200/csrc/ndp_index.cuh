@@ -916,11 +916,14 @@ struct IndexParams {
     int snap_depth;                   //   (0: always re-derive the sibling from the trail)
     short* trails;                    // [n_warps][trail_cap] working trail of each warp
     int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
-    int warp_bytes, off_pend;         // shared memory of one warp: state slot, then pend
+    int warp_bytes, off_pend;         // shared memory of one searcher: state slot, then pend
+    unsigned char* gstate;            // [searchers][warp_bytes] the same in global memory (lane-group kernel, kGlobal)
 };
 
-template <bool kPlain>
-__global__ void __launch_bounds__(128, 8) dfs_index_kernel(const __grid_constant__ IndexParams p) {
+// kMinBlocks: resident CTAs per SM the register allocation must allow (8: 64 registers, 32 warps per SM;
+// 12: 40 registers, 48 warps per SM -- for state slots small enough that shared memory holds 48 of them).
+template <bool kPlain, int kMinBlocks = 8>
+__global__ void __launch_bounds__(128, kMinBlocks) dfs_index_kernel(const __grid_constant__ IndexParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const IndexRoot& ix = p.ix;
     const unsigned lane = threadIdx.x & 31u;

@@ -23,8 +23,10 @@ namespace ndp {
 
 enum : int { GS_FETCH = 0, GS_UNIT = 1, GS_CHOOSE = 2, GS_DECIDE = 3, GS_BACK = 4, GS_FINISH = 5, GS_DONE = 6 };
 
-template <int L>
-__global__ void __launch_bounds__(128, 8) dfs_index_group_kernel(const __grid_constant__ IndexParams p) {
+// kGlobal: the searchers' state slots live in global memory (p.gstate, served by L1/L2) instead of shared
+// memory: the number of pieces in flight is then bounded by warps x groups, not by 228 KB / slot size.
+template <int L, bool kGlobal = false, int kMinBlocks = 8>
+__global__ void __launch_bounds__(128, kMinBlocks) dfs_index_group_kernel(const __grid_constant__ IndexParams p) {
     constexpr int G = 32 / L;
     constexpr unsigned kGroupBits = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(128, 8) dfs_index_group_kernel(const __grid_co
     const unsigned grp = lane / L, gl = lane % L, gbase = grp * L;
     const unsigned gmask = kGroupBits << gbase;
     const unsigned searcher0 = (blockIdx.x * (blockDim.x >> 5) + warp) * G;   // this warp's first searcher
-    unsigned char* warp_smem = smem_raw + (size_t)warp * G * p.warp_bytes;
+    unsigned char* warp_smem = kGlobal ? p.gstate + (size_t)searcher0 * p.warp_bytes : smem_raw + (size_t)warp * G * p.warp_bytes;
     // this lane's own group
     unsigned* B = reinterpret_cast<unsigned*>(warp_smem + (size_t)grp * p.warp_bytes);
     unsigned* table = B + ix.table_off;

@@ -11,17 +11,26 @@ import util_cnf
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["index", "index-whole", "scan"])
+@pytest.fixture(scope="module", params=["index", "index-whole", "index-global", "index-warp", "scan"])
 def nd(request):
-    """Every parity test runs once per DFS engine: all must match the oracle bit for bit.
+    """Every parity test runs once per DFS engine / kernel: all must match the oracle bit for bit.
     "index" cuts narrow shards into DFS-order pieces (automatic policy: every test frontier is
-    narrower than the device, so the split path is what runs); "index-whole" searches each
-    subproblem with one warp; "scan" is the clause-streaming engine."""
+    narrower than the device, so the split path is what runs) and, the test CNFs being small, searches
+    them with the lane-group kernel (4 pieces per warp, state slots in shared memory); "index-whole"
+    searches each subproblem whole; "index-global" forces the lane-group kernel with its state slots in
+    global memory (what large CNFs get); "index-warp" forces the one-piece-per-warp kernel; "scan" is the
+    clause-streaming engine."""
+    import os
     import ndp5_b200
     assert ndp5_b200.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
     ndp5_b200.set_engine(request.param.split("-")[0])
     ndp5_b200.set_split("off" if request.param == "index-whole" else "auto")
+    env = {"index-global": {"NDP_DFS_GLOBAL_STATE": "1"}, "index-warp": {"NDP_DFS_GROUPS": "1", "NDP_DFS_GLOBAL_STATE": "0"}}
+    for k, v in env.get(request.param, {}).items():
+        os.environ[k] = v
     yield ndp5_b200
+    for k in env.get(request.param, {}):
+        os.environ.pop(k, None)
     ndp5_b200.set_engine("auto")
     ndp5_b200.set_split("auto")
 
