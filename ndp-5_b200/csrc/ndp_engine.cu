@@ -1570,17 +1570,20 @@ struct SplitRun {
 // sizes, so large CNFs (deep subtrees) are cut finer -- the tail is what bounds an early-exit run.
 // n_root_clauses = 0: the coarse cut that shares a narrow frontier out over several devices (each device then
 // refines its share).  mean_alive = average live clauses per unit of the shard.
-size_t split_target(size_t n_sub, int n_warps, int n_root_clauses, double mean_alive) {
+size_t split_target(size_t n_sub, int n_warps, int n_root_clauses, double mean_alive, int groups = 1) {
     long long mode = g_split;
     if (mode < 0)
         if (const char* e = getenv("NDP_SPLIT")) mode = !strcmp(e, "off") ? 0 : atoll(e);
     if (mode == 0 || n_sub == 0) return 0;
     if (mode > 0) return (size_t)mode > n_sub ? (size_t)mode : 0;
-    size_t per_warp = n_root_clauses > 16384 ? 32 : n_root_clauses > 8192 ? 8 : 2;
+    // pieces per searcher (n_warps counts searchers: warps x lane groups).  Measured on the 48-bit CNF, 28416 searchers
+    // per B200: 2 / 4 / 8 / 16 pieces each -> cut 4 / 10 / 17 / 34 ms, search 502 / 453 / 435 / 406 ms on one GPU; with the
+    // work shared by 8 GPUs the cut costs the same and the tail is 8 x shorter, so 4 is the better compromise.
+    size_t per_warp = n_root_clauses > 16384 ? 32 : n_root_clauses > 8192 ? 4 : groups > 1 ? 1 : 2;
     if (n_root_clauses > 0)
         if (const char* e = getenv("NDP_SPLIT_PER_WARP")) per_warp = (size_t)std::max(1, atoi(e));
     if (n_sub >= per_warp * (size_t)n_warps) return 0;
-    const bool starved = 4 * n_sub < (size_t)n_warps;
+    const bool starved = 4 * n_sub < (size_t)n_warps / (size_t)std::max(groups, 1);   // fewer units than a quarter of the WARPS
     const bool deep = n_root_clauses <= 0 || mean_alive > 0.5 * (double)n_root_clauses;
     return starved || deep ? per_warp * (size_t)n_warps : 0;
 }
@@ -1717,7 +1720,7 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
     // index engine: a shard too narrow for the device is first cut into pieces in DFS order
     SplitRun split;
     if (use_index) {
-        const size_t target = split_target(n_sub, n_warps, ix->n_root, irep->mean_alive);
+        const size_t target = split_target(n_sub, n_warps, ix->n_root, irep->mean_alive, iplan.groups);
         if (target > n_sub && (rc = run_split(device, *ix, *irep, target, split, stats))) return rc;
     }
     const size_t nl = split.active ? split.n_pieces : n_sub;         // units the DFS kernel pulls
@@ -2417,7 +2420,7 @@ int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_e
         // (split_target's test: shard starved or subproblems still deep).  Each rank then refines its own
         // share down to pieces-per-warp granularity inside dfs_on_device -- in parallel, on its own data.
         const size_t n_warps = (size_t)iplan.searchers() * world;
-        size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive);
+        size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive, iplan.groups);
         if (g_split < 0 && !getenv("NDP_SPLIT")) {            // automatic policy
             const size_t coarse = (size_t)4096 * world;
             target = (world > 1 && target > run->n_sub && coarse > run->n_sub) ? coarse : 0;
@@ -2569,8 +2572,8 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         double alive = 0;
         for (const Entry& e : f->entries) alive += (double)e.n;
         alive /= (double)f->entries.size();
-        const bool worth = 4 * f->entries.size() < (size_t)n_warps * n_gpus || alive > 0.5 * (double)ix->n_root;
-        const size_t target = worth ? split_target(f->entries.size(), n_warps * n_gpus, 0, alive) : 0;
+        const bool worth = 4 * f->entries.size() < (size_t)n_warps / iplan.groups * n_gpus || alive > 0.5 * (double)ix->n_root;
+        const size_t target = worth ? split_target(f->entries.size(), n_warps * n_gpus, 0, alive, iplan.groups) : 0;
         if (target > f->entries.size()) {
             if (stats) memset(stats, 0, sizeof *stats);
             SplitRun split;
