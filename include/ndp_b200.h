@@ -140,7 +140,10 @@ void ndp_frontier_free(ndp_frontier* f);
  *   lowest after this shard.
  * winner: global index of the lowest SAT subproblem of this shard, or SIZE_MAX.
  * model/model_len: choices_k ++ DFS choices of the winner -- final_choices_i of NDP:1430-1431;
- *   model must hold model_cap ints.
+ *   model must hold model_cap ints.  One case returns a winner WITHOUT a model (model_len = 0): a lower SAT
+ *   index was already known when this shard's winner finished (the *exit_flag hint on entry, or a peer's exit
+ *   word) -- the job's model then comes from the shard that owns that lower index, and this shard's own SAT
+ *   subproblem is only reported in verdict[] / winner.
  * nodes/evals (may be NULL): per-subproblem counters, ndp_frontier_size entries each. */
 int ndp_dfs_shard(ndp_frontier* f, size_t first, size_t stride, int early_exit, size_t* exit_flag,
                   uint8_t* verdict, size_t* winner, int32_t* model, size_t model_cap, size_t* model_len,
