@@ -1865,6 +1865,15 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         CUDA_TRY(cudaMemcpy(h_reb.data(), b_reb.p, nl * 4, cudaMemcpyDeviceToHost));
         d2h += nl * (1 + 8 + 8 + 4);
     }
+    if (const char* dump = getenv("NDP_DUMP_PIECES")) {   // diagnostic: live clauses at the start of each unit vs nodes it took
+        std::vector<BfsNode> h_meta(nl1);
+        const BfsNode* d_meta = use_index ? (split.active ? split.sp.lv[split.side].meta : irep->d_meta) : nullptr;
+        if (d_meta && nl && cudaMemcpy(h_meta.data(), d_meta, nl * sizeof(BfsNode), cudaMemcpyDeviceToHost) == cudaSuccess)
+            if (FILE* fp = fopen(dump, "w")) {
+                for (size_t q = 0; q < nl; ++q) fprintf(fp, "%d,%d,%llu\n", h_meta[q].n, h_meta[q].kind, h_nodes[q]);
+                fclose(fp);
+            }
+    }
     std::vector<uint8_t> sub_v;
     std::vector<unsigned long long> sub_nodes, sub_evals;
     std::vector<unsigned> h_bestp;

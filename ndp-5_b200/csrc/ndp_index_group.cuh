@@ -268,26 +268,38 @@ __global__ void __launch_bounds__(128, kMinBlocks) dfs_index_group_kernel(const 
             }
         }
         __syncwarp();
-        const unsigned total = __reduce_add_sync(gmask, acc);
+        // group-wide sum by butterfly: redux.sync with four different member masks compiles to a loop over the masks
+        // (ncu: 4 REDUX per step); log2(L) shuffles do it in one pass (flags: <= L x 2^26 stays below 2^32)
+        unsigned total = acc;
+#pragma unroll
+        for (int off = 1; off < L; off <<= 1) total += __shfl_xor_sync(kFullMask, total, off);
         if (run) {
             n_live -= (int)(total & (kConflBit - 1u));
             if (n_live == 0) { verdict = 1; status = GS_FINISH; }        // empty branch => model (NDP:843-852 / 863-872)
             else if ((total >> 26) != 0u) status = GS_BACK;              // a clause reached three zeros
         }
         // ---- choice(): the first unit clause through the B[2] summary, L summary words per round
-        bool look = status == GS_UNIT;
+        // Each lane reads up to kRounds summary words (gl, gl + L, ...: independent loads), one ballot per round names
+        // the group's first non-zero word; no loop-carried vote, no second trip through the planes.
+        const bool look = status == GS_UNIT;
         int c = -1;
-        for (int sb = 0; sb < ix.sum_words; sb += L) {
-            const unsigned sw = (look && sb + (int)gl < ix.sum_words) ? B[ix.sum_off + sb + gl] : 0u;
-            const unsigned m = (__ballot_sync(kFullMask, sw != 0u) >> gbase) & kGroupBits;
-            const int s = m ? __ffs(m) - 1 : 0;
-            const unsigned word = __shfl_sync(kFullMask, sw, gbase + s);
-            if (look && m) {
-                const int w = (sb + s) * 32 + __ffs(word) - 1;
-                c = w * 32 + __ffs(B[w] & B[ix.bm_words + w]) - 1;
-                look = false;
+        {
+            constexpr int kRounds = 32 / L;              // sum_words <= 32
+            unsigned sw_sel = 0u;                        // the summary word of this lane in the round that hit
+            int hit = -1;                                // index (in words of the summary) of the first non-zero word
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+                if (r * L >= ix.sum_words) break;        // warp-uniform
+                const int i = r * L + (int)gl;
+                const unsigned sw = (look && i < ix.sum_words) ? B[ix.sum_off + i] : 0u;
+                const unsigned m = (__ballot_sync(kFullMask, sw != 0u) >> gbase) & kGroupBits;
+                if (hit < 0 && m) { hit = r * L + __ffs(m) - 1; sw_sel = sw; }
             }
-            if (ix.sum_words <= L || !__any_sync(kFullMask, look)) break;
+            const unsigned word = __shfl_sync(kFullMask, sw_sel, gbase + (hit >= 0 ? (unsigned)hit % L : 0u));
+            if (look && hit >= 0) {
+                const int w = hit * 32 + __ffs(word) - 1;
+                c = w * 32 + __ffs(B[w] & B[ix.bm_words + w]) - 1;
+            }
         }
         // ---- the literal of that clause: the LAST one still there; lanes 0..2 of the group test one each
         {
