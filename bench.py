@@ -580,6 +580,14 @@ def run_b200(args, workload):
             prof = recorded_profile(other)
             prof_note = " [capture of %s, same kernel build; no ncu capture of this workload]" % other
         ipn = prof.get("warp_instructions_per_node")
+        # real DRAM bytes of one DFS launch on one GPU (ncu): the capture's own figure for this workload, else bytes per node x nodes
+        traffic = None
+        if not prof_note and prof.get("dram_bytes_per_dfs_launch") and world == 1:
+            traffic = prof["dram_bytes_per_dfs_launch"]
+        elif not prof_note and prof.get("dram_bytes_per_node"):
+            traffic = prof["dram_bytes_per_node"] * nodes / world
+        elif not prof_note and prof.get("dram_bytes_per_dfs_launch"):
+            traffic = prof["dram_bytes_per_dfs_launch"] / world
         sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else 1965.0e6
         issue = None
         if ipn:
@@ -604,9 +612,8 @@ def run_b200(args, workload):
                                  "clause-eval counts asserted against reference-produced fixtures on every run"},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": prof.get("dram_bytes_per_dfs_launch") if not prof_note else None, "peak_source": peak_src,
-                         "traffic_frac": (prof["dram_bytes_per_dfs_launch"] / (prof["kernel_ms_under_ncu"] / 1e3) / 1e9 / peak
-                                          if not prof_note and prof.get("dram_bytes_per_dfs_launch") and prof.get("kernel_ms_under_ncu") else None),
+                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic_frac": traffic / dfs_s / 1e9 / peak if traffic else None,
                          "kernel": "the DFS kernel (dfs_index_group_kernel: 4 searches per warp), %.3f ms per launch incl. the cut "
                                    "(CUDA events on the launching stream)" % dfs_ms,
                          "algorithmic": "%d clause evaluations per step x 12 B (SURVEY.md §8d), counted by the device and "

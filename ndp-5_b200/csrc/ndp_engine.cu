@@ -1777,6 +1777,8 @@ int dfs_on_device(ndp_frontier* f, int device, size_t first, size_t stride, int 
         }
         p.best_piece = b_bestp.as<unsigned int>();
         p.first = first; p.stride = stride; p.n_local = nl;
+        p.max_steps = 0;
+        if (const char* e = getenv("NDP_PROFILE_MAX_STEPS")) p.max_steps = (unsigned)std::max(0ll, atoll(e));   // profiling knob (group kernel)
         if (const char* e = getenv("NDP_PROFILE_MAX_UNITS"))   // profiling knob: search only the first units (the rest stay NOT_RUN)
             p.n_local = std::min<unsigned long long>(nl, (unsigned long long)std::max(1ll, atoll(e)));
         p.next = b_next.as<unsigned int>();

@@ -918,6 +918,7 @@ struct IndexParams {
     int32_t* models;                  // [n_warps][trail_cap] trail parked by the warp holding the lowest model
     int warp_bytes, off_pend;         // shared memory of one searcher: state slot, then pend
     unsigned char* gstate;            // [searchers][warp_bytes] the same in global memory (lane-group kernel, kGlobal)
+    unsigned max_steps;               // profiling knob (0 = off): a warp gives up after this many unit steps (pieces left NOT_RUN)
 };
 
 // kMinBlocks: resident CTAs per SM the register allocation must allow (8: 64 registers, 32 warps per SM;

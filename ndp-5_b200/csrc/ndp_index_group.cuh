@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) dfs_index_group_kernel(const 
                     if (p.progress) *(volatile unsigned*)p.progress = qq;
                 }
                 qq = __shfl_sync(kFullMask, qq, 0);
-                if (qq >= p.n_local) {
+                if (qq >= p.n_local || (p.max_steps && steps >= p.max_steps)) {
                     if (mine) status = GS_DONE;
                 } else {
                     const unsigned oo = p.orig ? (unsigned)p.orig[qq] : qq;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) dfs_index_group_kernel(const 
         if ((++steps & 63u) == 0u) {     // every 64 steps: has a lower model become known?  (one vote: the group must agree)
             const bool gone = status == GS_UNIT && ((p.early_exit && *(volatile unsigned long long*)p.best < gq) ||
                                                     *(volatile unsigned int*)(p.best_piece + o) < q);
-            if (__ballot_sync(kFullMask, gone) & gmask) {
+            if ((__ballot_sync(kFullMask, gone) & gmask) || (p.max_steps && steps >= p.max_steps && status == GS_UNIT)) {
                 verdict = 2;             // abandon the piece
                 status = GS_FINISH;
             }

@@ -1,12 +1,5 @@
-set -x
-CMD="python bench.py --steps 1 --warmup 3 --no-tts --no-cpu-baseline"
-$CMD > gpurun_out/r2_plain_e.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_v8.csv $CMD > gpurun_out/r2_ncu_e.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dfs_index_group_kernel -s 3 -c 1 -o gpurun_out/r2_dfs_group_global_48bit $CMD > gpurun_out/r2_ncu_f.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dfs_split_kernel -s 3 -c 1 -o gpurun_out/r2_dfs_split_48bit $CMD > gpurun_out/r2_ncu_g.log 2>&1
-export NDP_PROFILE_MAX_UNITS=30000
+export NDP_PROFILE_MAX_STEPS=20000
 CMD3="python tools/ncu_probe.py rsaFACT-64bit 4096"
-$CMD3 > gpurun_out/r2_probe64.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dfs_index_group_kernel -s 1 -c 1 -o gpurun_out/r2_dfs_group_global_64bit $CMD3 > gpurun_out/r2_ncu_h.log 2>&1
-cat gpurun_out/r2_probe64.log | tail -2
-ls -la gpurun_out/r2_dfs_group_global* gpurun_out/r2_dfs_split_48bit*
+timeout 150 $CMD3 > gpurun_out/r2_probe64.log 2>&1 && \
+timeout 400 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.per_cycle_active,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,launch__registers_per_thread,launch__grid_size --clock-control none -k regex:dfs_index_group_kernel -s 1 -c 1 --csv --log-file gpurun_out/r2_dfs_group_global_64bit_metrics.csv $CMD3 > gpurun_out/r2_ncu_h.log 2>&1
+tail -1 gpurun_out/r2_probe64.log; tail -1 gpurun_out/r2_ncu_h.log; tail -16 gpurun_out/r2_dfs_group_global_64bit_metrics.csv | cut -d, -f12-

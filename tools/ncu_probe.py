@@ -2,8 +2,9 @@
 """One short DFS launch on a large CNF for `ncu --set full` (a full 64-bit launch runs for minutes; ncu replays a
 kernel ~40 times).  NDP_PROFILE_MAX_UNITS caps the launch at the first K pieces; everything else is the product path.
 
-    NDP_PROFILE_MAX_UNITS=20000 python tools/ncu_probe.py rsaFACT-64bit 4096
-Prints nodes, clause evals and kernel ms of the capped launch (divide the ncu instruction count by `nodes`)."""
+    NDP_PROFILE_MAX_STEPS=20000 python tools/ncu_probe.py rsaFACT-64bit 4096     (every warp stops after 20000 unit steps)
+    NDP_PROFILE_MAX_UNITS=20000 python tools/ncu_probe.py rsaFACT-64bit 4096     (only the first 20000 pieces are searched)
+Prints the nodes the DFS kernel visited in the capped launch (divide the ncu instruction count by `kernel_nodes`)."""
 import json
 import os
 import sys
@@ -20,11 +21,18 @@ def main(name, q):
     A = bench.clause_array(name)[0]
     fr = nd.bfs(A, 0, True, int(q))
     out = None
+    dump = "/tmp/ncu_probe_pieces.csv"
+    os.environ["NDP_DUMP_PIECES"] = dump
     for _ in range(2):      # the first launch warms the pools and the code; profile the second (ncu -s 1 -c 1)
         r = fr.dfs_shard(early_exit=False, counters=True)
+        kernel_nodes = 0
+        with open(dump) as f:            # nodes the DFS kernel itself visited (the cut's interior nodes are not its work)
+            for line in f:
+                kernel_nodes += int(line.rsplit(",", 1)[1])
         out = {"cnf": name, "q": int(q), "frontier": len(fr), "units_cap": os.environ.get("NDP_PROFILE_MAX_UNITS"),
-               "nodes": int(r["stats"]["nodes"]), "clause_evals": int(r["stats"]["clause_evals"]),
-               "kernel_ms": r["stats"]["kernel_ms"], "launches": int(r["stats"]["launches"])}
+               "steps_cap": os.environ.get("NDP_PROFILE_MAX_STEPS"), "kernel_nodes": kernel_nodes,
+               "nodes_incl_cut": int(r["stats"]["nodes"]), "kernel_ms_incl_cut": r["stats"]["kernel_ms"],
+               "launches": int(r["stats"]["launches"])}
     print(json.dumps(out))
     fr.free()
 
