@@ -181,7 +181,7 @@ int ndp_dfs_shard_shared(ndp_frontier* f, size_t first, size_t stride, int early
  * or its subproblems are heavy-tailed; these three calls share out PIECES instead.  Every rank holds the
  * whole frontier (each ran the deterministic BFS, as every reference rank does, NDP:1651) and makes the
  * SAME DFS-order cut of it into pieces (ndp_set_split policy, sized for world devices); rank r searches
- * pieces r, r + world, ... -- tens of thousands of small units per rank, so the ranks finish together.
+ * pieces r, r + world, ... -- hundreds to tens of thousands of near-equal units per rank, so the ranks finish together.
  * Results are per-piece and fold back per subproblem with two tiny collectives the CALLER runs (the
  * library holds no communicator):
  *   ndp_dfs_pieces_begin  cut + search this rank's pieces.  first_model[k] (ndp_frontier_size entries) =

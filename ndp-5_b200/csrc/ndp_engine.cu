@@ -2429,13 +2429,15 @@ int ndp_dfs_pieces_begin(ndp_frontier* f, size_t rank, size_t world, int early_e
         IndexLaunchPlan iplan;
         if ((rc = plan_index(f->device, *ix, f->max_var, iplan))) return rc;
         // The job-wide cut is made by EVERY rank (replicated work), so it is coarse: enough pieces for the
-        // static deal piece -> rank to balance statistically (>= 4096 per rank), and only where cutting pays
+        // static deal piece -> rank to balance statistically (>= 512 per rank: the subproblems of a granulated
+        // multiplier CNF are nearly uniform -- reference node counts, tests/golden/big_*.npz: cv 0.001-0.03 on the
+        // 48-bit frontiers, 0.2 on the 32-bit ones -- so 512 per rank already balance to well under 1 %), and only where cutting pays
         // (split_target's test: shard starved or subproblems still deep).  Each rank then refines its own
         // share down to pieces-per-warp granularity inside dfs_on_device -- in parallel, on its own data.
         const size_t n_warps = (size_t)iplan.searchers() * world;
         size_t target = split_target(run->n_sub, (int)std::min<size_t>(n_warps, 1u << 24), ix->n_root, rep->mean_alive, iplan.groups);
         if (g_split < 0 && !getenv("NDP_SPLIT")) {            // automatic policy
-            const size_t coarse = (size_t)4096 * world;
+            const size_t coarse = (size_t)512 * world;
             target = (world > 1 && target > run->n_sub && coarse > run->n_sub) ? coarse : 0;
         }
         if (target > run->n_sub) {

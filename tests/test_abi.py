@@ -44,6 +44,16 @@ def test_invalid_arguments_are_rejected_without_a_device():
     assert nd.lib.ndp_dfs_shard(None, 0, 1, 0, None, None, None, None, 0, None, None, None, None) == nd.NDP_E_INVALID
 
 
+def test_progress_and_piece_calls_reject_bad_arguments_without_a_device():
+    import ctypes as C
+    import ndp5_b200 as nd
+    assert nd.dfs_progress() == (0, 0, 0)                      # nothing is searching
+    h = C.c_void_p(None)
+    assert nd.lib.ndp_dfs_pieces_begin(None, 0, 1, 0, None, None, 0, C.byref(h), None, None) == nd.NDP_E_INVALID
+    assert nd.lib.ndp_dfs_pieces_fold(None, None, None, None, None, None, None, 0, None, None) == nd.NDP_E_INVALID
+    nd.lib.ndp_dfs_pieces_end(None)                            # a no-op, like free(NULL)
+
+
 def test_no_cpu_fallback_when_no_gpu():
     """Where there is no CUDA device the compute entry points must fail with NDP_E_CUDA."""
     import ndp5_b200 as nd
