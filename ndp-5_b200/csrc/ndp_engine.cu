@@ -760,10 +760,11 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
         coop_warps = (int)std::min<size_t>(32, (200 * 1024) / slot_bytes);
         if (const char* e = getenv("NDP_PERSIST_WARPS")) coop_warps = std::max(1, std::min(coop_warps, atoi(e)));
         if (coop && coop_warps >= 4) {
-            CUDA_TRY(cudaFuncSetAttribute(bfs_index_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            const void* pkern = ix->plain ? (const void*)bfs_index_persistent_kernel<true> : (const void*)bfs_index_persistent_kernel<false>;
+            CUDA_TRY(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(coop_warps * slot_bytes)));
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_index_persistent_kernel, coop_warps * 32,
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pkern, coop_warps * 32,
                                                                    coop_warps * slot_bytes));
             if (per_sm >= 1) {
                 coop_grid = std::min(sms, 160);   // PersistScratch holds 160 CTA records
@@ -843,7 +844,8 @@ int ndp_bfs(const int32_t* clauses3, size_t n_clauses, int max_iterations, int o
                 short* ppaths = d_ppaths.as<short>();
                 void* args[] = {&ixv, &a0, &a1, &n0, &n1, &t0, &t1, &chd, &tp, &tl, &Dv, &Qv, &ovrv, &maxl, &dps, &dsc,
                                 &snaps, &ppaths, &window_max, &max_block_nodes};
-                cudaError_t le = cudaLaunchCooperativeKernel((const void*)bfs_index_persistent_kernel, dim3(coop_grid),
+                cudaError_t le = cudaLaunchCooperativeKernel(ix->plain ? (const void*)bfs_index_persistent_kernel<true>
+                                                                       : (const void*)bfs_index_persistent_kernel<false>, dim3(coop_grid),
                                                              dim3(coop_warps * 32), args, coop_warps * slot_bytes, 0);
                 if (le == cudaSuccess) le = cudaStreamSynchronize(0);
                 if (le != cudaSuccess) { status = fail(NDP_E_CUDA, std::string("BFS persistent kernel: ") + cudaGetErrorString(le)); break; }
@@ -1606,9 +1608,10 @@ int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica&
     sp.warp_bytes = sp.off_chain + (int)align16((size_t)sp.chain_cap * 2);
     const int warps = (int)std::min<size_t>(32, ((size_t)200 * 1024) / (size_t)sp.warp_bytes);
     if (!coop || warps < 1) return NDP_OK;   // cannot co-schedule the grid: search the subproblems whole
-    CUDA_TRY(cudaFuncSetAttribute(dfs_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * sp.warp_bytes));
+    const void* skern = ix.plain ? (const void*)dfs_split_kernel<true> : (const void*)dfs_split_kernel<false>;
+    CUDA_TRY(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * sp.warp_bytes));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfs_split_kernel, warps * 32,
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, skern, warps * 32,
                                                            (size_t)warps * sp.warp_bytes));
     if (per_sm < 1) return NDP_OK;
     const size_t cap = 2 * (size_t)sp.target;                 // pieces per level (children of a level: <= cap)
@@ -1662,7 +1665,7 @@ int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica&
     split_init_kernel<<<(int)std::min<size_t>((n_sub + 255) / 256, 1024), 256>>>(sp, rep.d_slot_ptr, rep.d_meta, (int)n_sub);
     CUDA_TRY(cudaGetLastError());
     void* args[] = {&sp};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dfs_split_kernel, dim3(sms), dim3(warps * 32), args,
+    CUDA_TRY(cudaLaunchCooperativeKernel(skern, dim3(sms), dim3(warps * 32), args,
                                          (size_t)warps * sp.warp_bytes, 0));
     CUDA_TRY(cudaMemcpy(&st, sp.st, sizeof st, cudaMemcpyDeviceToHost));
     run.active = true;

@@ -343,6 +343,7 @@ __device__ __forceinline__ void slot_load_cg(unsigned* dst_shared, const unsigne
 // buffer together with what choice() returns for it.  Per-child metadata as in bfs_expand_kernel.
 // One node: stage the parent's slot in S (shared), apply each attempted branch, write open
 // children to dst slots 2j / 2j+1.  ch[0] = LA, ch[1] = RA.
+template <bool kPlain = false>
 __device__ __forceinline__ void index_expand_node(const IndexRoot& ix, const unsigned* src,   // no __restrict__:
                                                   unsigned* dst, int j, const BfsNode nd, unsigned* S,   // a persistent kernel re-reads what it wrote
 
@@ -363,11 +364,11 @@ __device__ __forceinline__ void index_expand_node(const IndexRoot& ix, const uns
         __syncwarp();
         if (lane == 0) table_set(table, t);
         bool conflict;
-        const int n_after = index_assign<true>(ix, S, nd.n, t, conflict, lane);
+        const int n_after = index_assign<true, kPlain>(ix, S, nd.n, t, conflict, lane);
         if (n_after == 0) ch[b].empty = 1;
         if (n_after > 0 && !conflict) {
             int kind, lit;
-            index_choice(ix, S, table, n_after, lane, kind, lit);
+            index_choice<kPlain>(ix, S, table, n_after, lane, kind, lit);
             ch[b].n = n_after; ch[b].kind = kind; ch[b].lit = lit;
             slot_copy(dst + ((size_t)2 * j + b) * ix.slot_words, S, ix.slot_words, lane);
         }
@@ -447,6 +448,7 @@ struct PersistScratch {           // zeroed by the host before every launch
 // One node, K levels down (K > 1).  Outputs e = 0..count-1 in queue order: state slot
 // dst[kWindowFan * j + e], metadata children[kWindowFan * j + e], choices paths[(kWindowFan * j + e) * kWindowMax + r].
 // Returns the output count, or -1 if the node needs more than kWindowFan outputs / kWindowPend snapshots.
+template <bool kPlain = false>
 __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsigned* src, unsigned* dst, int j,
                                                  const BfsNode nd, unsigned* S, unsigned* snap, unsigned lane, int K, int fan,
                                                  BfsChild* children, short* paths, unsigned& my_exp, unsigned& my_push,
@@ -501,12 +503,12 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
                     __syncwarp();
                     if (lane == 0) table_set(table, t);
                     bool conflict;
-                    const int n2 = index_assign<true>(ix, S, n_live, t, conflict, lane);
+                    const int n2 = index_assign<true, kPlain>(ix, S, n_live, t, conflict, lane);
                     if (n2 > 0 && !conflict) {
                         if ((int)lane == r) ++my_push;   // NDP:912,923
                         if ((int)lane == r) my_path = t;
                         n_live = n2;
-                        index_choice(ix, S, table, n_live, lane, kind, lit);
+                        index_choice<kPlain>(ix, S, table, n_live, lane, kind, lit);
                         ++r;
                     } else {
                         backtrack = true; // empty (a dropped solution leaf) or conflict: not pushed
@@ -526,14 +528,15 @@ __device__ __forceinline__ int index_window_node(const IndexRoot& ix, const unsi
         __syncwarp();
         if (lane == 0) table_set(table, -pv);
         bool conflict;
-        n_live = index_assign<true>(ix, S, pn, -pv, conflict, lane);   // known open and non-empty
+        n_live = index_assign<true, kPlain>(ix, S, pn, -pv, conflict, lane);   // known open and non-empty
         if ((int)lane == pr) my_path = -pv;
-        index_choice(ix, S, table, n_live, lane, kind, lit);
+        index_choice<kPlain>(ix, S, table, n_live, lane, kind, lit);
         r = pr + 1;
     }
     return out;
 }
 
+template <bool kPlain>
 __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexRoot ix, unsigned* sbuf0, unsigned* sbuf1,
                                                                    BfsNode* nodes0, BfsNode* nodes1, int32_t* ntree0,
                                                                    int32_t* ntree1, BfsChild* children,
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
             }
             if (K == 1) {
                 BfsChild ch[2];
-                index_expand_node(ix, src, dst, j, nd, S, lane, ch);
+                index_expand_node<kPlain>(ix, src, dst, j, nd, S, lane, ch);
                 if (lane == 0) {
                     children[2 * j] = ch[0];
                     children[2 * j + 1] = ch[1];
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(1024) bfs_index_persistent_kernel(const IndexR
                     if (nd.n > 0 && var != 0) { atomicAdd(&s_exp[0], 1u); atomicAdd(&s_ev[0], (unsigned long long)nd.n); }
                 }
             } else {
-                const int c = index_window_node(ix, src, dst, j, nd, S, snap, lane, K, fan, children, paths, my_exp, my_push, my_br, my_ev);
+                const int c = index_window_node<kPlain>(ix, src, dst, j, nd, S, snap, lane, K, fan, children, paths, my_exp, my_push, my_br, my_ev);
                 if (lane == 0) {
                     s_cnt[k] = (unsigned char)(c < 0 ? 0 : c);
                     if (c < 0) s_overflow = 1u;

@@ -95,6 +95,7 @@ __global__ void split_init_kernel(const SplitParams p, const unsigned* const* sl
     }
 }
 
+template <bool kPlain>
 __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur, int j, unsigned* S, short* chain,
                                                    unsigned lane) {
     const IndexRoot& ix = p.ix;
@@ -160,10 +161,10 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
             if (lane == 0) { chain[nchain] = (short)t; table_set(table, t); }
             ++nchain;
             bool conflict;
-            n_live = index_assign<true>(ix, S, n_live, t, conflict, lane);
+            n_live = index_assign<true, kPlain>(ix, S, n_live, t, conflict, lane);
             if (n_live == 0) { outcome = SPLIT_LEAF; break; }        // NDP:843-852 / 863-872
             if (conflict) { outcome = SPLIT_DEAD; break; }
-            index_choice(ix, S, table, n_live, lane, kind, lit);
+            index_choice<kPlain>(ix, S, table, n_live, lane, kind, lit);
         }
         par.outcome = outcome;
         par.chain_nodes = cn;
@@ -192,17 +193,17 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
             __syncwarp();
             bool conflict;
             if (lane == 0) table_set(table, -v);
-            int n_c = index_assign<true>(ix, S, n_live, -v, conflict, lane);
+            int n_c = index_assign<true, kPlain>(ix, S, n_live, -v, conflict, lane);
             int k_c, l_c;
-            index_choice(ix, S, table, n_c, lane, k_c, l_c);
+            index_choice<kPlain>(ix, S, table, n_c, lane, k_c, l_c);
             ch[0].n = n_c; ch[0].kind = k_c; ch[0].lit = l_c;
             slot_copy(d0, S, ix.slot_words, lane);
             __syncwarp();
             slot_load_cg(S, d1, ix.slot_words, lane);
             __syncwarp();
             if (lane == 0) table_set(table, v);
-            n_c = index_assign<true>(ix, S, n_live, v, conflict, lane);
-            index_choice(ix, S, table, n_c, lane, k_c, l_c);
+            n_c = index_assign<true, kPlain>(ix, S, n_live, v, conflict, lane);
+            index_choice<kPlain>(ix, S, table, n_c, lane, k_c, l_c);
             ch[1].n = n_c; ch[1].kind = k_c; ch[1].lit = l_c;
             slot_copy(d1, S, ix.slot_words, lane);
         }
@@ -214,6 +215,7 @@ __device__ __forceinline__ void split_expand_piece(const SplitParams& p, int cur
     }
 }
 
+template <bool kPlain>
 __global__ void __launch_bounds__(1024) dfs_split_kernel(const __grid_constant__ SplitParams p) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(1024) dfs_split_kernel(const __grid_constant__
             return;   // uniform: every thread decided from the same committed state
         }
         // ---- expand: one warp per piece
-        for (int j = gwarp; j < m; j += total_warps) split_expand_piece(p, cur, j, S, chain, lane);
+        for (int j = gwarp; j < m; j += total_warps) split_expand_piece<kPlain>(p, cur, j, S, chain, lane);
         grid.sync();
         // ---- ordered compaction (CTA 0): open children keep their order; dead ends forward their counts
         if (blockIdx.x == 0) {
