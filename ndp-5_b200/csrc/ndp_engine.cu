@@ -152,8 +152,16 @@ double now_ms() {
 }
 bool tracing() { static const bool t = getenv("NDP_TRACE") != nullptr; return t; }
 
-struct DevBuf {  // tiny RAII for per-call device allocations
+struct DevBuf {  // tiny RAII for per-call device allocations (movable, not copyable)
     void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { if (p) dev_free(p); p = o.p; o.p = nullptr; }
+        return *this;
+    }
     ~DevBuf() { if (p) dev_free(p); }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
@@ -1590,8 +1598,8 @@ size_t split_target(size_t n_sub, int n_warps, int n_root_clauses, double mean_a
     return starved || deep ? per_warp * (size_t)n_warps : 0;
 }
 
-int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
-              ndp_stats* stats) {
+int run_split_once(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
+                   ndp_stats* stats) {
     const size_t n_sub = rep.n_local;
     int sms = 0, coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -1676,6 +1684,22 @@ int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica&
         fprintf(stderr, "[ndp_split] %zu subproblems -> %zu pieces in %d levels (exit %d), tree %llu, log %llu\n", n_sub,
                 run.n_pieces, st.levels_done, st.exit_reason, st.tree_count, st.log_count);
     return NDP_OK;
+}
+
+// The cut with a target that fits the device: the piece arenas are 4 x target state slots, and a large CNF on a
+// busy device may not have room for the target the policy asks for.  Out of memory halves the target (fewer, larger
+// pieces: same results, a longer tail) instead of failing the search; below the shard's own size there is no cut.
+int run_split(int device, const IndexRoot& ix, const ndp_frontier::IndexReplica& rep, size_t target, SplitRun& run,
+              ndp_stats* stats) {
+    for (;;) {
+        if (target <= rep.n_local) return NDP_OK;         // no room for any cut: the units are searched whole
+        int rc = run_split_once(device, ix, rep, target, run, stats);
+        if (rc != NDP_E_NOMEM) return rc;
+        cudaGetLastError();                                // clear the sticky allocation error
+        run = SplitRun();                                  // releases what the failed attempt had allocated
+        target /= 2;
+        if (tracing()) fprintf(stderr, "[ndp_split] out of device memory: retrying with a target of %zu pieces\n", target);
+    }
 }
 
 // One shard on one device.  `shared_best`/`peer_best`: early-exit words (this device's + peers').
