@@ -2614,8 +2614,15 @@ int ndp_dfs_batch(ndp_frontier* f, int n_gpus, int early_exit, uint8_t* verdict,
         double alive = 0;
         for (const Entry& e : f->entries) alive += (double)e.n;
         alive /= (double)f->entries.size();
+        // Same rule as ndp_dfs_pieces_begin: the job-wide cut is made on ONE device and its pieces travel to the others, so it
+        // is only made where the static deal of whole subproblems could not balance the devices (fewer than 512 each), and it is
+        // coarse (512 pieces per device); every device then refines its own share in parallel.
         const bool worth = 4 * f->entries.size() < (size_t)n_warps / iplan.groups * n_gpus || alive > 0.5 * (double)ix->n_root;
-        const size_t target = worth ? split_target(f->entries.size(), n_warps * n_gpus, 0, alive, iplan.groups) : 0;
+        size_t target = worth ? split_target(f->entries.size(), n_warps * n_gpus, 0, alive, iplan.groups) : 0;
+        if (g_split < 0 && !getenv("NDP_SPLIT")) {
+            const size_t coarse = (size_t)512 * n_gpus;
+            target = (target > f->entries.size() && coarse > f->entries.size()) ? coarse : 0;
+        }
         if (target > f->entries.size()) {
             if (stats) memset(stats, 0, sizeof *stats);
             SplitRun split;
