@@ -36,6 +36,22 @@ def test_header_cites_reference_lines():
         assert cite in text
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C11 (no C++ types in the signatures) and a C
+    program must link against the library."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "ndp_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { int n = -1; ndp_device_count(&n); printf("%s %d\\n", ndp_version(), n >= 0); return 0; }\n')
+    exe = tmp_path / "use"
+    lib = os.path.join(ROOT, "ndp-5_b200", "lib")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", lib, "-lndp_b200", "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ndp-b200")
+
+
 def test_invalid_arguments_are_rejected_without_a_device():
     import ndp5_b200 as nd
     assert nd.lib.ndp_bfs(None, 0, 1, 0, -1, None, None, None, None) == nd.NDP_E_INVALID
