@@ -97,26 +97,38 @@ Header scrape_header(const std::string& text) {
     static const std::regex re_bits(R"(Variables for second input \[msb,...,lsb\]: \[.*?,\s*(\d+)\])");  // NDP:1598
     static const std::regex re_first(R"(Variables for first input \[msb,...,lsb\]: \[(.*?)\])");        // NDP:948
     static const std::regex re_second(R"(Variables for second input \[msb,...,lsb\]: \[(.*?)\])");      // NDP:949
+    // std::stoi as the reference uses it (NDP:957-959, 1595-1600), but a number that does not convert is reported in
+    // Header::error with the reference's own message instead of leaving the function as an exception
+    auto to_int = [&](const std::string& tok, int& dst, const char* lead) {
+        try { dst = std::stoi(tok); return true; }
+        catch (const std::invalid_argument&) { if (h.error.empty()) h.error = std::string(lead) + "Invalid argument while converting to int: " + tok; }
+        catch (const std::out_of_range&) { if (h.error.empty()) h.error = std::string(lead) + "Out of range error while converting to int: " + tok; }
+        return false;
+    };
     if (std::regex_search(text, m, re_problem)) {
-        h.ok_problem = true;
-        h.num_vars = std::stoi(m[1].str());
-        h.num_clauses = std::stoi(m[2].str());
-        if (std::regex_search(text, m, re_bits)) h.num_bits = std::stoi(m[1].str());
+        h.ok_problem = to_int(m[1].str(), h.num_vars, "\n") & to_int(m[2].str(), h.num_clauses, "\n");
+        if (h.ok_problem && std::regex_search(text, m, re_bits)) to_int(m[1].str(), h.num_bits, "\n");
     }
     if (std::regex_search(text, m, re_product)) { h.ok_product = true; h.product = m[1].str(); }
-    auto list = [&](const std::regex& re, std::vector<int>& dst) {
+    auto list = [&](const std::regex& re, std::vector<int>& dst, const char* lead) {
         if (!std::regex_search(text, m, re)) return;
         std::istringstream iss(m[1].str());
         std::string tok;
-        while (std::getline(iss, tok, ',')) dst.push_back(std::stoi(tok));   // NDP:957-959
+        while (std::getline(iss, tok, ',')) {                                  // NDP:957-959
+            int v = 0;
+            if (!to_int(tok, v, lead)) return;                                 // (the reference rethrows here: NDP:960-966)
+            dst.push_back(v);
+        }
     };
-    list(re_first, h.v1);
-    list(re_second, h.v2);
+    list(re_first, h.v1, "\n");     // NDP:961 prints a leading newline for the first list only
+    list(re_second, h.v2, "");
     return h;
 }
 
 int calculate_max_iterations(int world_size, int num_clauses, int num_vars, int num_bits) {
-    return num_clauses - num_vars + ((world_size / 2) * num_bits);   // NDP:1034
+    // NDP:1034: num_clauses - num_vars + (world_size / 2) * num_bits, in unsigned arithmetic so that a nonsense header
+    // (a 10-digit "bit count") wraps as the reference's compiled code does instead of being undefined behaviour
+    return (int)((unsigned)num_clauses - (unsigned)num_vars + (unsigned)(world_size / 2) * (unsigned)num_bits);
 }
 
 std::string read_file(const std::string& path) {

@@ -29,6 +29,7 @@ struct Header {
     int num_vars = 0, num_clauses = 0, num_bits = 0;
     std::string product;            // decimal string
     std::vector<int> v1, v2;        // input variable lists, msb..lsb
+    std::string error;              // a header number that std::stoi refuses: the reference's message (it then terminates, NDP:960-966)
 };
 // the regexes of main() (NDP:1590-1615) and ExtractInputsFromDimacs (NDP:946-990)
 Header scrape_header(const std::string& text);

@@ -35,7 +35,7 @@ int ndph_scrape_header(const char* text, int* num_vars, int* num_clauses, int* n
     *n1 = h.v1.size(); *n2 = h.v2.size();
     for (size_t j = 0; j < h.v1.size() && j < vcap; ++j) v1[j] = h.v1[j];
     for (size_t j = 0; j < h.v2.size() && j < vcap; ++j) v2[j] = h.v2[j];
-    return !h.ok_problem ? 1 : !h.ok_product ? 2 : 0;
+    return !h.error.empty() ? 3 : !h.ok_problem ? 1 : !h.ok_product ? 2 : 0;   // 3: a header number std::stoi refuses
 }
 int ndph_calculate_max_iterations(int world, int clauses, int vars, int bits) {
     return calculate_max_iterations(world, clauses, vars, bits);

@@ -84,6 +84,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     const Header h = scrape_header(text);
+    if (!h.error.empty()) { std::cout << h.error << std::endl; return 1; }   // the reference prints this and terminates (NDP:960-966)
     if (!h.ok_problem) { std::cout << "\nError: Could not extract number of variables and clauses from DIMACS header.\n" << std::endl; return 1; }
     if (!h.ok_product) { std::cout << "\nError: Could not extract input number from DIMACS header.\n" << std::endl; return 1; }
 

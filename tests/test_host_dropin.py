@@ -13,6 +13,7 @@ import cbind
 import util_cnf
 
 HAVE_REF = cbind.RefLib.available()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -70,6 +71,27 @@ def test_header_known_answers(host, cnf_text):
     assert host.scrape_header("c nothing\n")["rc"] == 1                    # no problem line (NDP:1602-1605)
     assert host.calculate_max_iterations(8, 5664, 1440, 17) == 4292
     assert host.calculate_max_iterations(2, 1296, 336, 9) == 969
+    # header numbers std::stoi refuses: the reference prints a message and terminates (NDP:960-966, 1595-1600); the
+    # drop-in reports them (rc 3; the program prints the reference's message and exits 1) -- no exception, no abort
+    bad_list = cnf_text("rsaFACT-16bit").replace("[8, 7, 6,", "[8, x, 6,")
+    assert host.scrape_header(bad_list)["rc"] == 3
+    assert host.scrape_header("c Circuit for product = 15 [1111]\np cnf 99999999999999999999 2\n1 2 3 0\n")["rc"] == 3
+    assert host.calculate_max_iterations(10, 24, 40, 1100011011) == (24 - 40 + 5 * 1100011011) % 2**32   # = 1205087743: wraps, no UB
+
+
+def test_host_code_under_sanitizers(tmp_path):
+    """tools/fuzz_host.cpp: parser, header scrape, CLI, naming, factor decode and the BFS JSON writer / reader fed
+    mutated inputs under ASan + UBSan (a short run; `fuzz_host 30000` is the long one)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "fuzz_host")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-I" + os.path.join(ROOT, "ndp-5_b200", "host"), os.path.join(ROOT, "tools", "fuzz_host.cpp"),
+                           os.path.join(ROOT, "ndp-5_b200", "host", "ndp_host.cpp"), "-l:libgmp.so.10", "-o", exe])
+    r = subprocess.run([exe, "400"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "iterations ok" in r.stdout, r.stdout[-3000:]
 
 
 def test_naming_and_formatting_known_answers(host):
