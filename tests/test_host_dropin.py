@@ -63,6 +63,37 @@ def test_parser_reports_the_widths_the_reference_drops(host, ref):
     assert host.dropped("p cnf 3 1\n1 2 3 0\n") == (0, 0)
 
 
+def test_parser_differential_fuzz(host, ref, cnf_text):
+    """parse_dimacs against the reference's parseDimacsString (NDP:619-642) on mutated DIMACS text: junk tokens, signs,
+    overflowing integers, tabs / CR / vertical tabs, missing and doubled terminators, comment and problem lines in odd
+    places.  Same clause array, bit for bit."""
+    import random
+    rng = random.Random(7)
+    base = cnf_text("rsaFACT-16bit").splitlines()[:60]
+    tokens = ["0", "-", "+5", " ", "\t", "c", "p", "x", "1.5", "2147483647", "2147483648", "-2147483648", "-2147483649",
+              "99999999999999999999", "\r", "  7", "-0", "+0", "0 0", "1e3", "0x10", "--3", "+-3", "3-", "3 -", "\x0b", "\x0c"]
+    for it in range(600):
+        lines = list(base)
+        for _ in range(rng.randint(1, 6)):
+            i = rng.randrange(len(lines))
+            op = rng.randrange(5)
+            if op == 0:
+                lines[i] = lines[i] + " " + rng.choice(tokens)
+            elif op == 1:
+                lines[i] = rng.choice(tokens) + " " + lines[i]
+            elif op == 2:
+                parts = lines[i].split(" ")
+                parts.insert(rng.randrange(len(parts) + 1), rng.choice(tokens))
+                lines[i] = " ".join(parts)
+            elif op == 3:
+                lines.insert(i, " ".join(rng.choice(tokens) for _ in range(rng.randint(0, 5))))
+            else:
+                lines[i] = lines[i].replace(" ", rng.choice([" ", "  ", "\t", ""]), rng.randint(1, 3))
+        text = rng.choice(["\n", "\r\n"]).join(lines) + rng.choice(["", "\n", "\n\n"])
+        a, b = host.parse(text), ref.parse(text)
+        assert a.shape == b.shape and (a == b).all(), (it, text)
+
+
 def test_header_known_answers(host, cnf_text):
     h = host.scrape_header(cnf_text("rsaFACT-16bit"))
     assert (h["rc"], h["num_vars"], h["num_clauses"], h["num_bits"], h["product"]) == (0, 336, 1296, 9, "35611")
@@ -178,6 +209,56 @@ def test_report_matches_reference(host, ref, tmp_path, cnf_text):
         saved = re.search(r"Result saved: (.*)\n", want).group(1)
         assert os.path.basename(saved) == file_name
         assert open(saved).read() == file_text
+
+
+def test_report_and_naming_differential_fuzz(host, ref, tmp_path, cnf_text):
+    """Randomised differential of the report block (generate_output, NDP:1127-1205) and the naming / formatting helpers
+    (NDP:423-485, 533-562, 1093-1125) against the reference's own: boundary durations (59.995 s, 3599.999 s, ...), zero
+    totals, 40-digit inputs, file names with and without five-digit runs, dots and directories."""
+    import random
+    rng = random.Random(11)
+    hdr = ref.scrape_header(cnf_text("rsaFACT-16bit"))
+
+    def seconds():
+        if rng.random() < 0.3:
+            return rng.choice([0.0, 59.994, 59.995, 59.999, 60.0, 3599.999, 3600.0, 86399.5])
+        return rng.choice([rng.random(), rng.random() * 100, rng.random() * 10000, rng.random() * 1e6, rng.random() * 1e-4])
+
+    names = ["rsaFACT-16bit.dimacs", "n1234567890123.cnf", "a.b.c.cnf", "noext", "dir/sub/x.dimacs", "12345.cnf", "123456.cnf",
+             "x12345y678.cnf", "", ".cnf", "99999999999999999999.dimacs", "a b.cnf"]
+    for it in range(120):
+        found = rng.random() < 0.6
+        model = [rng.choice([-1, 1]) * rng.randint(1, 336) for _ in range(rng.randint(0, 40))] if found else []
+        bfs_s, dfs_s = seconds(), seconds()
+        bits, nv, nc = rng.randint(1, 70), rng.randint(1, 99999), rng.randint(1, 999999)
+        N = rng.choice([35611, 1, 0, 2 ** 64 - 59, 10 ** 40 + 7, 143])
+        fname, flag = rng.choice(names[:8]), rng.choice(["d60", "q4096", "auto", "d-1"])
+        iters, iq, wr, ws, fq = rng.randint(0, 10 ** 6), rng.randint(0, 10 ** 5), rng.randint(0, 64), rng.randint(1, 64), rng.randint(0, 10 ** 5)
+        want = ref.generate_output(found, model, bfs_s, dfs_s, bits, nv, nc, N, hdr["v1"], hdr["v2"], "NDP-5_6_7", fname, flag,
+                                   str(tmp_path), iters, iq, wr, ws, fq)
+        utc = re.search(r"Zulu time: (.*)\n", want).group(1)
+        got, file_text, file_name = host.report(found, model, bfs_s, dfs_s, bits, nv, nc, N, hdr["v1"], hdr["v2"], "NDP-5_6_7",
+                                                fname, flag, iters, iq, wr, ws, fq, utc)
+        assert got == want.split("Result saved:")[0], (it, fname, flag, bfs_s, dfs_s)
+        saved = re.search(r"Result saved: (.*)\n", want).group(1)
+        assert os.path.basename(saved) == file_name and open(saved).read() == file_text, (it, fname)
+    for it in range(1000):
+        x = seconds() * rng.choice([1, 1, 10, 1000])
+        assert host.format_duration(x) == ref.format_duration(x), x
+        a, b = seconds(), rng.choice([0.0, seconds()])
+        assert host.format_percentage(a, b) == ref.format_percentage(a, b), (a, b)
+    for n in names:
+        for flag in ["d12", "q4096", "auto", ""]:
+            for pid in ["af743d8f1e2ed8c6", "abc", ""]:
+                assert host.format_filename("NDP-5_6_7", n, pid, flag) == ref.format_filename("NDP-5_6_7", n, pid, flag), (n, flag, pid)
+                assert host.create_bfs_filename("NDP-5_6_7", n, pid, flag) == ref.create_bfs_filename("NDP-5_6_7", n, pid, flag)
+    for n in ["35611", "0", "", "123456789012345678901234567890", "abc"]:
+        for bits in [0, 9, 64]:
+            for w in [1, 2, 16]:
+                utc = "2025-01-01 00:00:00 UTC"
+                assert host.create_problem_id(n, bits, w, utc) == ref.create_problem_id(n, bits, w, utc)
+    for v in [[], [1], [1, -2, 3], list(range(-50, 50))]:
+        assert host.format_vector(v) == ref.format_vector(v)
 
 
 def test_report_known_answer(host, cnf_text):
