@@ -318,7 +318,8 @@ bool write_bfs_json(const std::string& path, size_t count, const ElementGetter& 
                 for (size_t j = 0; j < nch; ++j) { o.put("                "); o.put_int(ch[j]); o.put(j + 1 < nch ? ",\n" : "\n"); }
                 o.put("            ],\n");
             } else o.put("],\n");
-            o.put("            \"clauses\": [");
+            // an empty ClauseSet leaves serialized_clauses a default-constructed json: stock nlohmann prints null (NDP:498-503)
+            o.put(ncl ? "            \"clauses\": [" : "            \"clauses\": null\n");
             if (ncl) {
                 o.put("\n");
                 for (size_t c = 0; c < ncl; ++c) {
@@ -327,7 +328,7 @@ bool write_bfs_json(const std::string& path, size_t count, const ElementGetter& 
                     o.put(c + 1 < ncl ? "                ],\n" : "                ]\n");
                 }
                 o.put("            ]\n");
-            } else o.put("]\n");
+            }
             o.put(k + 1 < count ? "        },\n" : "        }\n");
         }
         o.put("    ],\n");
@@ -444,12 +445,16 @@ bool read_bfs_json(const std::string& path, BfsJson* out, std::string* err) {
             size_t n_before_cl = out->clauses3.size(), n_before_ch = out->choices.size();
             bool entry_ok = in.object([&](const std::string& k2) {
                 if (k2 == "choices") return in.array([&]() { int32_t v; if (!in.integer(v)) return false; out->choices.push_back(v); return true; });
-                if (k2 == "clauses")
+                if (k2 == "clauses") {
+                    // what the reference writes for an empty ClauseSet; its reader iterates a null as empty (NDP:519-522)
+                    in.ws();
+                    if (in.peek() == 'n') return in.skip_value();
                     return in.array([&]() {
                         int got = 0;
                         bool a = in.array([&]() { int32_t v; if (!in.integer(v)) return false; if (got < 3) out->clauses3.push_back(v); ++got; return true; });
                         return a && got == 3;
                     });
+                }
                 return in.skip_value();
             });
             (void)n_before_cl; (void)n_before_ch;

@@ -289,9 +289,9 @@ def test_bfs_json_layout_is_stock_nlohmann_dump4(host, oracle, tmp_path, cnf_tex
                     '                    0,\n                    12,\n                    -20\n                ],\n'
                     '                [\n                    0,\n                    -12,\n                    20\n'
                     '                ]\n            ]\n        },\n        {\n            "choices": [],\n'
-                    '            "clauses": []\n        }\n    ],\n    "bfs_time": 1.5\n}')
+                    '            "clauses": null\n        }\n    ],\n    "bfs_time": 1.5\n}')       # empty ClauseSet: null, as the reference writes it
     assert json.loads(text) == {"bfs_results": [{"choices": [17, 81, -88], "clauses": [[0, 12, -20], [0, -12, 20]]},
-                                                {"choices": [], "clauses": []}], "bfs_time": 1.5}
+                                                {"choices": [], "clauses": None}], "bfs_time": 1.5}
     p2 = str(tmp_path / "empty.json")
     assert host.write_bfs_json(p2, [], 0.0) == 0
     assert open(p2).read() == '{\n    "bfs_time": 0.0\n}'       # empty frontier omits bfs_results
@@ -343,6 +343,40 @@ def test_bfs_json_cross_reads_with_reference(host, ref, oracle, tmp_path, cnf_te
         assert t == 1.5 and len(back) == len(items)
         assert all((a == c).all() and (b == d).all() for (a, b), (c, d) in zip(items, back))
         ref.frontier_free(h)
+
+
+def test_bfs_json_differential_fuzz(host, ref, tmp_path):
+    """Random frontiers (empty clause sets -- which the reference writes as `"clauses": null` --, empty choices, INT_MIN /
+    INT_MAX literals, odd bfs_time values) through both writers and both readers: ours -> readBFSResults (NDP:600-612),
+    saveBFSResults (NDP:564-598) -> ours."""
+    import random
+    rng = random.Random(5)
+    ext = [0, 1, -1, 2 ** 31 - 1, -2 ** 31, 32766, -32767, 65536]
+
+    def lit():
+        return rng.choice(ext) if rng.random() < 0.2 else rng.randint(-5000, 5000)
+
+    def same(a, b):
+        return len(a) == len(b) and all(x[0].reshape(-1, 3).tolist() == y[0].reshape(-1, 3).tolist() and
+                                        x[1].tolist() == y[1].tolist() for x, y in zip(a, b))
+    for it in range(80):
+        items = []
+        for k in range(rng.choice([1, 2, 5, 17])):
+            ncl, nch = rng.choice([0, 0, 1, 3, 40]), rng.choice([0, 1, 7, 300])
+            items.append((np.array([[lit(), lit(), lit()] for _ in range(ncl)], np.int32).reshape(-1, 3),
+                          np.array([lit() for _ in range(nch)], np.int32)))
+        t = rng.choice([0.0, 1.5, 0.0134, 123456.789, 1e-7, 3.0, 1e20, 0.1])
+        p = str(tmp_path / "ours.json")
+        assert host.write_bfs_json(p, items, t) == 0
+        h, t2 = ref.read_bfs(p)
+        got = ref.frontier_list(h)
+        ref.frontier_free(h)
+        assert t2 == t and same(got, items), it
+        h = ref.frontier_from_arrays(items)
+        name = ref.save_bfs(h, "NDP-5_6_7", "x.cnf", "af743d8f1e2ed8c6", "q5", str(tmp_path), t)
+        ref.frontier_free(h)
+        back, t3 = host.read_bfs_json(str(tmp_path / name))
+        assert t3 == t and same(back, items), it
 
 
 def test_bfs_json_reader_rejects_fractional_literals(host, tmp_path):
