@@ -118,9 +118,13 @@ def test_host_code_under_sanitizers(tmp_path):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     exe = str(tmp_path / "fuzz_host")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
-                           "-I" + os.path.join(ROOT, "ndp-5_b200", "host"), os.path.join(ROOT, "tools", "fuzz_host.cpp"),
-                           os.path.join(ROOT, "ndp-5_b200", "host", "ndp_host.cpp"), "-l:libgmp.so.10", "-o", exe])
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         "-I" + os.path.join(ROOT, "ndp-5_b200", "host"), os.path.join(ROOT, "tools", "fuzz_host.cpp"),
+                         os.path.join(ROOT, "ndp-5_b200", "host", "ndp_host.cpp"), "-l:libgmp.so.10", "-o", exe],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if cc.returncode != 0 and ("asan" in cc.stdout or "ubsan" in cc.stdout):
+        pytest.skip("sanitizer runtimes not installed")
+    assert cc.returncode == 0, cc.stdout[-3000:]
     r = subprocess.run([exe, "400"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "iterations ok" in r.stdout, r.stdout[-3000:]
 
