@@ -10,7 +10,7 @@ come from the plain-C oracle port AFTER its node count was checked equal to the 
 Cases (subproblem subsets are index lists into the reference's own frontier):
   rsaFACT-32bit_q16384   every subproblem (exhaustive): the old bench headline
   prime-32bit_q16384     every subproblem (all UNSAT)
-  rsaFACT-48bit_q4096    every 64th subproblem (heavy-tailed sizes: an interleaved sample), then
+  rsaFACT-48bit_q4096    every 8th subproblem (an interleaved sample: 512 of 4096, ~70 min on 6 cores incl. the port), then
                          (second file, *_prefix) indices 0..first_sat so that "lowest SAT index" is pinned
   rsaFACT-48bit_q65536   indices 0..first_sat+1 (BASELINE configs[2]; the reference BFS alone takes ~17 min)
 Each .npz holds: index (int64), verdict (uint8), nodes (int64), evals (uint64), and the BFS
@@ -138,7 +138,7 @@ def case_sample_then_prefix(ref, refp, cnf, value, every, first_sat_claim, prefi
 CASES = {
     "rsaFACT-32bit_q16384": lambda ref, refp: case_exhaustive(ref, refp, "rsaFACT-32bit", 16384),
     "prime-32bit_q16384": lambda ref, refp: case_exhaustive(ref, refp, "prime-32bit", 16384),
-    "rsaFACT-48bit_q4096": lambda ref, refp: case_sample_then_prefix(ref, refp, "rsaFACT-48bit", 4096, 64, 301),
+    "rsaFACT-48bit_q4096": lambda ref, refp: case_sample_then_prefix(ref, refp, "rsaFACT-48bit", 4096, 8, 301),
     "rsaFACT-48bit_q65536": lambda ref, refp: case_sample_then_prefix(ref, refp, "rsaFACT-48bit", 65536, 0, 4822,
                                                                      sample=False),
 }
