@@ -10,9 +10,11 @@ come from the plain-C oracle port AFTER its node count was checked equal to the 
 Cases (subproblem subsets are index lists into the reference's own frontier):
   rsaFACT-32bit_q16384   every subproblem (exhaustive): the old bench headline
   prime-32bit_q16384     every subproblem (all UNSAT)
-  rsaFACT-48bit_q4096    every 8th subproblem (an interleaved sample: 512 of 4096, ~70 min on 6 cores incl. the port), then
+  rsaFACT-48bit_q4096    every 8th subproblem (an interleaved sample: 512 of 4096, ~70 min on 6 cores incl. the port; the
+                         committed file also holds 4, 20, 36, ... from a second run merged in: 768), then
                          (second file, *_prefix) indices 0..first_sat so that "lowest SAT index" is pinned
-  rsaFACT-48bit_q65536   indices 0..first_sat+1 (BASELINE configs[2]; the reference BFS alone takes ~17 min)
+  rsaFACT-48bit_q65536   indices 0..first_sat+1 (BASELINE configs[2]; the reference BFS alone takes ~17 min); the committed
+                         big_rsaFACT-48bit_q65536.npz adds every 128th subproblem from 4879 on (same functions, run by hand)
 Each .npz holds: index (int64), verdict (uint8), nodes (int64), evals (uint64), and the BFS
 counters iterations / task_count / size / bfs_clause_evals, plus cnf / mode / value as strings.
 """
